@@ -1,0 +1,185 @@
+/*
+ * nerf_b200.h -- C ABI of libnerf_b200.so: the B200 (sm_100a) implementation of torch-NeRF's per-ray
+ * rendering hot path.  Plain pointers and sizes only; no torch types cross this boundary.
+ *
+ * The reference (DveloperY0115/torch-NeRF) is pure Python and has no FFI of its own: its "plugin API"
+ * is the Python class protocol selected by config strings in torch_nerf/runners/runner_utils.py:526-660.
+ * Each entry point below states the reference interface it stands behind (paths relative to the
+ * reference root).  The Python mirror of those classes lives in torch-nerf_b200/ and binds these
+ * symbols with ctypes (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - every pointer named *_dev / documented "device" is a CUDA device pointer owned by the caller
+ *     (the Python side allocates with torch); the library never frees or keeps caller buffers.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no hidden syncs.
+ *   - return value: 0 = ok, NERF_ERR_ARG = bad argument (the Python mirror raises ValueError with the
+ *     reference's semantics before calling), NERF_ERR_CUDA = CUDA failure (RuntimeError).
+ *     nerf_last_error() returns a thread-local message for the last non-zero return.
+ *   - float = IEEE binary32.  Row-major, contiguous unless a leading dimension is given.
+ */
+#ifndef NERF_B200_H
+#define NERF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NERF_OK 0
+#define NERF_ERR_ARG 1
+#define NERF_ERR_CUDA 2
+
+typedef void* nerf_stream_t; /* cudaStream_t */
+
+/* ------------------------------------------------------------------------------------------------
+ * library / device
+ * ---------------------------------------------------------------------------------------------- */
+int nerf_version(void);
+const char* nerf_last_error(void);
+/* fills SM count and compute capability of the current device */
+int nerf_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1 ray generation
+ *   replaces RaySamplerBase.generate_rays  (src/renderer/ray_samplers/sampler_base.py:134-197,
+ *   _get_ray_directions :70-113, map_rays_to_ndc :199-257) fed from PerspectiveCamera
+ *   (src/renderer/cameras.py:84-153).  Directions are not normalised; NDC keeps the reference's
+ *   formula (no origin shift to the near plane).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  float fx, fy, cx, cy;  /* intrinsic[0][0], [1][1], [0][2], [1][2] */
+  float rot[9];          /* c2w[:3,:3], row-major */
+  float trans[3];        /* c2w[:3,3] */
+  float ndc_sx;          /* (float)(-(2*focal/img_w))   (python-double arithmetic, then float) */
+  float ndc_sy;          /* (float)(-(2*focal/img_h)) */
+  float ndc_two_near;    /* (float)(2*t_near) */
+  int32_t img_w, img_h;
+  int32_t project_to_ndc;
+} nerf_camera_t;
+
+/* coords_dev: (N,2) int64 screen coordinates (u=col, v=H-1-row), as VolumeRenderer.screen_coords holds them */
+int nerf_generate_rays(const int64_t* coords_dev, int64_t n, const nerf_camera_t* cam, float* ray_o_dev,
+                       float* ray_d_dev, nerf_stream_t stream);
+/* pixel_idx_dev: (N,) int64 flat pixel ids p = row*W + col (volume_renderer.py:171-190 folded in);
+ * NULL means p = first_pixel + i (whole-frame render, volume_renderer.py:129-133). */
+int nerf_generate_rays_from_pixels(const int64_t* pixel_idx_dev, int64_t first_pixel, int64_t n,
+                                   const nerf_camera_t* cam, float* ray_o_dev, float* ray_d_dev,
+                                   nerf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2 / K3 sampling along rays
+ *   replaces StratifiedSampler.sample_along_rays (src/renderer/ray_samplers/stratified_sampler.py:17-128)
+ *   and sample_pdf (src/renderer/ray_samplers/utils.py:8-58).
+ *   The uniforms are INPUTS (drawn by the caller in the reference's order: coarse pass rand_like(N,Sc);
+ *   fine pass rand_like(N,Sc), rand(N,Sf), rand_like(N,Sf)) so results are replayable bit for bit.
+ * ---------------------------------------------------------------------------------------------- */
+/* host helper: bins[i] of torch.linspace(t_near, t_far, S+1)[:-1] (stratified_sampler.py:156-161) and
+ * step = (float)((t_far - t_near) / S) (:162).  bins_host has room for num_partitions floats. */
+int nerf_make_bins(double t_near, double t_far, int num_partitions, float* bins_host, float* step_out);
+
+/* The sampling kernels evaluate the bins in-kernel with the same float32 formula as nerf_make_bins, so they
+ * take (t_near, t_far) instead of a table.
+ *
+ * coarse branch (:91-128).  Any of t/pts/dirs/delta outputs may be NULL (not materialised). */
+int nerf_sample_coarse(const float* ray_o_dev, const float* ray_d_dev, int64_t n, int num_samples, double t_near,
+                       double t_far, const float* u_dev, float* t_dev, float* pts_dev, float* dirs_dev,
+                       float* delta_dev, nerf_stream_t stream);
+
+/* sample_pdf (utils.py:8-58).  weights_dev (N,Sc) is modified IN PLACE (+= 1e-5), like the reference.
+ * idx_dev (N,Sf) int64 = searchsorted(cdf, u1, right=True) - 1, may be NULL. */
+int nerf_sample_pdf(double t_near, double t_far, float* weights_dev, const float* u1_dev, const float* u2_dev,
+                    int64_t n, int num_coarse, int num_fine, float* t_fine_dev, int64_t* idx_dev,
+                    nerf_stream_t stream);
+
+/* hierarchical branch (:57-90 + :112-128): fresh coarse draw (u0), importance samples (u1,u2), sort,
+ * deltas, points.  Outputs have S = num_coarse + num_fine samples per ray; any may be NULL. */
+int nerf_sample_fine(const float* ray_o_dev, const float* ray_d_dev, int64_t n, int num_coarse, int num_fine,
+                     double t_near, double t_far, float* weights_dev, const float* u0_dev, const float* u1_dev,
+                     const float* u2_dev, int64_t* idx_dev, float* t_dev, float* pts_dev, float* dirs_dev,
+                     float* delta_dev, nerf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K4 positional encoding
+ *   replaces PositionalEncoder.encode (src/signal_encoder/positional_encoder.py:49-104):
+ *   [x | sin(2^0 x) | cos(2^0 x) | ...], no pi.  out row stride ld_out >= out_dim floats.
+ * ---------------------------------------------------------------------------------------------- */
+int nerf_posenc(const float* x_dev, int64_t m, int in_dim, int embed_level, int include_input, float* out_dev,
+                int64_t ld_out, nerf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K7 / K8 alpha compositing
+ *   replaces QuadratureIntegrator.integrate_along_rays (src/renderer/integrators/quadrature_integrator.py:14-67)
+ *   and its autograd backward.  depth = sum w_i t_i and opacity = sum w_i are additions with no reference
+ *   counterpart (t_dev/depth_dev/opacity_dev may be NULL).
+ * ---------------------------------------------------------------------------------------------- */
+int nerf_composite_fwd(const float* sigma_dev, const float* radiance_dev, const float* delta_dev,
+                       const float* t_dev, int64_t n, int s, float* rgb_dev, float* w_dev, float* depth_dev,
+                       float* opacity_dev, nerf_stream_t stream);
+/* g_w_dev (N,S) may be NULL (zero upstream gradient on the weights, the training case) */
+int nerf_composite_bwd(const float* sigma_dev, const float* radiance_dev, const float* delta_dev,
+                       const float* g_rgb_dev, const float* g_w_dev, int64_t n, int s, float* g_sigma_dev,
+                       float* g_radiance_dev, nerf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K5 / K6 NeRF MLP
+ *   replaces NeRF.forward (src/network/nerf.py:65-121) and its autograd backward.
+ *   params: host array of 22 device pointers in state_dict order
+ *     fc_in.weight, fc_in.bias, fc_1.weight, fc_1.bias, ... fc_9.weight, fc_9.bias, fc_out.weight, fc_out.bias
+ *   weights are (out,in) row-major fp32, exactly nn.Linear's layout (nerf.py:49-59).
+ * ---------------------------------------------------------------------------------------------- */
+#define NERF_NUM_PARAM_TENSORS 22
+
+typedef struct {
+  int32_t pos_dim;  /* 63 */
+  int32_t view_dim; /* 27 */
+  int32_t feat_dim; /* 256 */
+} nerf_mlp_dims_t;
+
+/* -- fp32 validation mode (CUDA-core SGEMM chain; the <=1e-3 parity gate runs on this) -- */
+/* floats of activation cache per call of m rows (forward writes it, backward reads it) */
+size_t nerf_mlp_f32_cache_floats(const nerf_mlp_dims_t* dims, int64_t m);
+/* floats of scratch needed by backward */
+size_t nerf_mlp_f32_bwd_scratch_floats(const nerf_mlp_dims_t* dims, int64_t m);
+/* pos_dev (M,pos_dim), view_dev (M,view_dim): ENCODED inputs, as NeRF.forward takes them */
+int nerf_mlp_f32_forward(const nerf_mlp_dims_t* dims, const float* const* params, const float* pos_dev,
+                         const float* view_dev, int64_t m, float* sigma_dev, float* rgb_dev, float* cache_dev,
+                         nerf_stream_t stream);
+/* grads: host array of 22 device pointers (same order/shapes as params); OVERWRITTEN with dL/dparam */
+int nerf_mlp_f32_backward(const nerf_mlp_dims_t* dims, const float* const* params, const float* cache_dev,
+                          const float* rgb_dev, int64_t m, const float* g_sigma_dev, const float* g_rgb_dev,
+                          float* const* grads, float* scratch_dev, nerf_stream_t stream);
+
+/* -- bf16 tensor-core mode (tcgen05 / TMEM, fp32 accumulation; pos 63 / view 27 / feat 256 only) -- */
+/* bytes of the packed weight image (bf16, K-major 128B-swizzled tiles, forward + transposed copies) */
+size_t nerf_mlp_bf16_packed_bytes(void);
+/* re-pack after every optimizer step */
+int nerf_mlp_bf16_pack(const float* const* params, void* packed_dev, nerf_stream_t stream);
+/* bytes of per-call training cache for m rows (saved activations in tile-image form + relu masks) */
+size_t nerf_mlp_bf16_cache_bytes(int64_t m);
+/* Fused query: positional encoding of pts/dirs (K4) is computed inside the kernel as the first layer's
+ * operand (cube.py:62-74 + nerf.py:65-121).  pts_dev/dirs_dev (M,3) fp32 RAW (un-encoded).
+ * Alternatively pts_dev == NULL and rays are given: row r = ray (r / s), sample (r % s), point =
+ * o + t*d, view dir = d  (then t_dev (N,S), ray_o_dev/ray_d_dev (N,3), s = samples per ray).
+ * cache_dev == NULL -> inference (nothing saved). */
+int nerf_mlp_bf16_forward(const void* packed_dev, const float* pts_dev, const float* dirs_dev,
+                          const float* ray_o_dev, const float* ray_d_dev, const float* t_dev, int s, int64_t m,
+                          float* sigma_dev, float* rgb_dev, void* cache_dev, nerf_stream_t stream);
+size_t nerf_mlp_bf16_bwd_scratch_bytes(int64_t m);
+int nerf_mlp_bf16_backward(const void* packed_dev, const void* cache_dev, const float* rgb_dev, int64_t m,
+                           const float* g_sigma_dev, const float* g_rgb_dev, float* const* grads,
+                           void* scratch_dev, nerf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * self tests of the tensor-core building blocks (used by tests/ on the GPU box)
+ * ---------------------------------------------------------------------------------------------- */
+/* D(128 x n) = A(128 x k) * B(n x k)^T with one tcgen05 tile; a/b bf16 bits row-major, d fp32 row-major.
+ * variant selects operand majors: 0 = K-major/K-major, 1 = MN-major A and B (wgrad form). */
+int nerf_selftest_umma(const uint16_t* a_dev, const uint16_t* b_dev, float* d_dev, int n, int k, int variant,
+                       nerf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERF_B200_H */

@@ -1,0 +1,298 @@
+// K4 positional encoding (standalone, for the drop-in encoder and parity checks) and K7/K8 alpha compositing.
+//
+// Reference behaviour restated (paths relative to the reference root, torch_nerf/src/...):
+//   signal_encoder/positional_encoder.py:49-104          [x | sin(2^l x) | cos(2^l x)]_l, no pi
+//   renderer/integrators/quadrature_integrator.py:14-67  x = sigma*delta, T = exp(-exclusive cumsum), w = T(1-e^-x)
+//
+// Both are HBM-bound: 384 B/sample (encoding), 24 B/sample forward and 40 B/sample backward (compositing).
+// Compositing is one warp per ray; the transmittance prefix is a float64 shuffle scan whose per-element
+// partial sums are rounded to float32 exactly like torch's CPU cumsum, and it is a TRUE exclusive scan
+// (shifted), never inclusive-minus-own: delta_last = 1e8 would cancel catastrophically.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace nerf {
+
+// ------------------------------------------------------------------------------------------------
+// K4
+// ------------------------------------------------------------------------------------------------
+constexpr int kEncRows = 64;  // rows per CTA
+
+__global__ void __launch_bounds__(256)
+    posenc_kernel(const float* __restrict__ x, int64_t m, int c, int levels, int include_input,
+                  float* __restrict__ out, int64_t ld_out) {
+  extern __shared__ float tile[];  // [kEncRows][out_dim]
+  const int out_dim = c * (2 * levels + (include_input ? 1 : 0));
+  const int64_t row0 = (int64_t)blockIdx.x * kEncRows;
+  const int rows = (int)min((int64_t)kEncRows, m - row0);
+  const int shift = include_input ? c : 0;
+  // one thread per (row, channel): coalesced read of the (rows, c) slab
+  for (int e = threadIdx.x; e < rows * c; e += blockDim.x) {
+    int r = e / c, ch = e - r * c;
+    float v = __ldg(x + (row0 * c) + e);
+    float* dst = tile + r * out_dim;
+    if (include_input) dst[ch] = v;
+    float f = 1.0f;
+    for (int l = 0; l < levels; ++l) {
+      float s, co;
+      sincosf(__fmul_rn(f, v), &s, &co);  // freq * x is exact (power of two); full-range reduction
+      dst[shift + (2 * l) * c + ch] = s;
+      dst[shift + (2 * l + 1) * c + ch] = co;
+      f *= 2.0f;
+    }
+  }
+  __syncthreads();
+  if (ld_out == out_dim) {
+    float* dst = out + row0 * ld_out;
+    for (int e = threadIdx.x; e < rows * out_dim; e += blockDim.x) dst[e] = tile[e];
+  } else {
+    for (int e = threadIdx.x; e < rows * out_dim; e += blockDim.x) {
+      int r = e / out_dim, k = e - r * out_dim;
+      out[(row0 + r) * ld_out + k] = tile[e];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7 / K8
+// ------------------------------------------------------------------------------------------------
+constexpr int kCompWarps = 4;
+
+__device__ __forceinline__ double shfl_up_f64(double v, int d) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_up_sync(0xffffffffu, lo, d);
+  hi = __shfl_up_sync(0xffffffffu, hi, d);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_down_f64(double v, int d) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_down_sync(0xffffffffu, lo, d);
+  hi = __shfl_down_sync(0xffffffffu, hi, d);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_f64(double v, int src) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_sync(0xffffffffu, lo, src);
+  hi = __shfl_sync(0xffffffffu, hi, src);
+  return __hiloint2double(hi, lo);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+// loads the 32x3 radiance block of one chunk through shared memory (coalesced), returns this lane's rgb
+__device__ __forceinline__ void load_rgb_chunk(const float* __restrict__ src, int cnt, float* stage, float& r,
+                                               float& g, float& b) {
+  const int lane = lane_id();
+  __syncwarp();
+  for (int e = lane; e < 3 * cnt; e += 32) stage[e] = __ldg(src + e);
+  __syncwarp();
+  if (lane < cnt) {
+    r = stage[3 * lane], g = stage[3 * lane + 1], b = stage[3 * lane + 2];
+  } else {
+    r = g = b = 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(kCompWarps * 32)
+    composite_fwd_kernel(const float* __restrict__ sigma, const float* __restrict__ radiance,
+                         const float* __restrict__ delta, const float* __restrict__ tvals, int64_t n, int s,
+                         float* __restrict__ rgb_out, float* __restrict__ w_out, float* __restrict__ depth_out,
+                         float* __restrict__ opacity_out) {
+  __shared__ float stage_all[kCompWarps][96];
+  const int warp = threadIdx.x >> 5, lane = lane_id();
+  float* stage = stage_all[warp];
+  int64_t ray = (int64_t)blockIdx.x * kCompWarps + warp;
+  if (ray >= n) return;
+  double carry = 0.0;   // float64 running sum of x over previous chunks
+  float prev_csum = 0.f;  // float32-rounded inclusive sum up to the previous chunk's last element
+  float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_d = 0.f, acc_o = 0.f;
+  for (int base = 0; base < s; base += 32) {
+    const int i = base + lane;
+    const bool ok = i < s;
+    const int cnt = min(32, s - base);
+    float x = 0.f;
+    if (ok) x = __fmul_rn(__ldg(sigma + ray * s + i), __ldg(delta + ray * s + i));  // :41
+    // inclusive float64 scan of x within the chunk
+    double inc = (double)x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      double up = shfl_up_f64(inc, d);
+      if (lane >= d) inc += up;
+    }
+    inc += carry;
+    float csum = (float)inc;  // torch cumsum output element (float32)
+    // exclusive = previous element's (rounded) inclusive sum  (:44-52)
+    float excl = __shfl_up_sync(0xffffffffu, csum, 1);
+    if (lane == 0) excl = prev_csum;
+    float trans = expf(-excl);
+    float alpha = __fsub_rn(1.0f, expf(-x));  // :55
+    float w = ok ? __fmul_rn(trans, alpha) : 0.f;  // :58
+    if (ok && w_out) w_out[ray * s + i] = w;
+    float r, g, b;
+    load_rgb_chunk(radiance + (ray * s + base) * 3, cnt, stage, r, g, b);
+    acc_r = fmaf(w, r, acc_r);
+    acc_g = fmaf(w, g, acc_g);
+    acc_b = fmaf(w, b, acc_b);
+    if (depth_out && ok) acc_d = fmaf(w, __ldg(tvals + ray * s + i), acc_d);
+    acc_o += w;
+    carry = shfl_f64(inc, 31);
+    prev_csum = __shfl_sync(0xffffffffu, csum, 31);
+  }
+  acc_r = warp_sum(acc_r), acc_g = warp_sum(acc_g), acc_b = warp_sum(acc_b);
+  if (depth_out) acc_d = warp_sum(acc_d);
+  if (opacity_out) acc_o = warp_sum(acc_o);
+  if (lane == 0) {
+    rgb_out[3 * ray + 0] = acc_r;
+    rgb_out[3 * ray + 1] = acc_g;
+    rgb_out[3 * ray + 2] = acc_b;
+    if (depth_out) depth_out[ray] = acc_d;
+    if (opacity_out) opacity_out[ray] = acc_o;
+  }
+}
+
+// Backward of w_i = T_i (1 - e^{-x_i}), rgb = sum w_i c_i, x = sigma*delta:
+//   g_c_i = w_i g_rgb;  g_w_i = g_rgb . c_i (+ external);  g_x_i = g_w_i T_{i+1} - sum_{k>i} g_w_k w_k;  g_sigma_i = delta_i g_x_i
+// with T_{i+1} = T_i e^{-x_i}.  Forward quantities are recomputed (24 B/sample read instead of 28).
+// Chunks are walked from the far end so the suffix sum is a running carry (true exclusive suffix scan);
+// the prefix sums of x needed for T are taken from a first pass that stores the chunk totals.
+__global__ void __launch_bounds__(kCompWarps * 32)
+    composite_bwd_kernel(const float* __restrict__ sigma, const float* __restrict__ radiance,
+                         const float* __restrict__ delta, const float* __restrict__ g_rgb,
+                         const float* __restrict__ g_w_ext, int64_t n, int s, float* __restrict__ g_sigma,
+                         float* __restrict__ g_radiance) {
+  __shared__ float stage_all[kCompWarps][96];
+  __shared__ double chunk_tot[kCompWarps][64];  // up to 2048 samples per ray
+  const int warp = threadIdx.x >> 5, lane = lane_id();
+  float* stage = stage_all[warp];
+  int64_t ray = (int64_t)blockIdx.x * kCompWarps + warp;
+  if (ray >= n) return;
+  const float gr = __ldg(g_rgb + 3 * ray), gg = __ldg(g_rgb + 3 * ray + 1), gb = __ldg(g_rgb + 3 * ray + 2);
+  const int nchunk = (s + 31) / 32;
+  // pass 1: float64 totals of x per chunk -> exclusive chunk offsets
+  {
+    double run = 0.0;
+    for (int c = 0; c < nchunk; ++c) {
+      int i = c * 32 + lane;
+      float x = (i < s) ? __fmul_rn(__ldg(sigma + ray * s + i), __ldg(delta + ray * s + i)) : 0.f;
+      double v = (double)x;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v += shfl_down_f64(v, d);
+      v = shfl_f64(v, 0);
+      if (lane == 0) chunk_tot[warp][c] = run;  // sum of all x before this chunk
+      run += v;
+    }
+  }
+  __syncwarp();
+  double suffix = 0.0;  // sum_{k > last element of this chunk} g_w_k w_k
+  for (int c = nchunk - 1; c >= 0; --c) {
+    const int base = c * 32;
+    const int i = base + lane;
+    const bool ok = i < s;
+    const int cnt = min(32, s - base);
+    float sg = 0.f, dl = 0.f;
+    if (ok) {
+      sg = __ldg(sigma + ray * s + i);
+      dl = __ldg(delta + ray * s + i);
+    }
+    float x = __fmul_rn(sg, dl);
+    double inc = (double)x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      double up = shfl_up_f64(inc, d);
+      if (lane >= d) inc += up;
+    }
+    inc += chunk_tot[warp][c];
+    float csum = (float)inc;
+    float excl = __shfl_up_sync(0xffffffffu, csum, 1);
+    if (lane == 0) excl = (c == 0) ? 0.f : (float)chunk_tot[warp][c];
+    float trans = expf(-excl);
+    float ex = expf(-x);
+    float w = ok ? __fmul_rn(trans, __fsub_rn(1.0f, ex)) : 0.f;
+    float r, g, b;
+    load_rgb_chunk(radiance + (ray * s + base) * 3, cnt, stage, r, g, b);
+    float gw = gr * r + gg * g + gb * b;
+    if (g_w_ext && ok) gw += __ldg(g_w_ext + ray * s + i);
+    // exclusive suffix scan of gw*w inside the chunk (float64), plus the carry from later chunks
+    double p = ok ? (double)gw * (double)w : 0.0;
+    double sfx = p;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      double dn = shfl_down_f64(sfx, d);
+      if (lane + d < 32) sfx += dn;
+    }
+    double sfx_excl = shfl_down_f64(sfx, 1);
+    if (lane == 31) sfx_excl = 0.0;
+    sfx_excl += suffix;
+    if (ok) {
+      float gx = (float)((double)gw * (double)(trans * ex) - sfx_excl);
+      g_sigma[ray * s + i] = dl * gx;
+    }
+    // g_c = w * g_rgb, staged for coalesced stores
+    __syncwarp();
+    if (ok) {
+      stage[3 * lane] = w * gr;
+      stage[3 * lane + 1] = w * gg;
+      stage[3 * lane + 2] = w * gb;
+    }
+    __syncwarp();
+    float* dst = g_radiance + (ray * s + base) * 3;
+    for (int e = lane; e < 3 * cnt; e += 32) dst[e] = stage[e];
+    suffix += shfl_f64(sfx, 0);
+  }
+}
+
+}  // namespace nerf
+
+using namespace nerf;
+
+extern "C" {
+
+int nerf_posenc(const float* x_dev, int64_t m, int in_dim, int embed_level, int include_input, float* out_dev,
+                int64_t ld_out, nerf_stream_t stream) {
+  NERF_CHECK_ARG(x_dev && out_dev, "nerf_posenc: null pointer");
+  NERF_CHECK_ARG(m >= 0 && in_dim > 0 && embed_level >= 0 && embed_level <= 32, "nerf_posenc: bad sizes");
+  const int out_dim = in_dim * (2 * embed_level + (include_input ? 1 : 0));
+  NERF_CHECK_ARG(out_dim > 0 && ld_out >= out_dim, "nerf_posenc: ld_out smaller than the encoding width");
+  if (m == 0) return NERF_OK;
+  size_t smem = sizeof(float) * kEncRows * out_dim;
+  NERF_CHECK_ARG(smem <= 200 * 1024, "nerf_posenc: encoding too wide");
+  if (smem > 48 * 1024)
+    NERF_CUDA(cudaFuncSetAttribute(posenc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  posenc_kernel<<<(unsigned)ceil_div64(m, kEncRows), 256, smem, as_stream(stream)>>>(x_dev, m, in_dim, embed_level,
+                                                                                   include_input, out_dev, ld_out);
+  NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
+
+int nerf_composite_fwd(const float* sigma_dev, const float* radiance_dev, const float* delta_dev,
+                       const float* t_dev, int64_t n, int s, float* rgb_dev, float* w_dev, float* depth_dev,
+                       float* opacity_dev, nerf_stream_t stream) {
+  NERF_CHECK_ARG(sigma_dev && radiance_dev && delta_dev && rgb_dev, "nerf_composite_fwd: null pointer");
+  NERF_CHECK_ARG(n >= 0 && s > 0, "nerf_composite_fwd: bad sizes");
+  NERF_CHECK_ARG(depth_dev == nullptr || t_dev != nullptr, "nerf_composite_fwd: depth needs t");
+  if (n == 0) return NERF_OK;
+  composite_fwd_kernel<<<(unsigned)ceil_div64(n, kCompWarps), kCompWarps * 32, 0, as_stream(stream)>>>(
+      sigma_dev, radiance_dev, delta_dev, t_dev, n, s, rgb_dev, w_dev, depth_dev, opacity_dev);
+  NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
+
+int nerf_composite_bwd(const float* sigma_dev, const float* radiance_dev, const float* delta_dev,
+                       const float* g_rgb_dev, const float* g_w_dev, int64_t n, int s, float* g_sigma_dev,
+                       float* g_radiance_dev, nerf_stream_t stream) {
+  NERF_CHECK_ARG(sigma_dev && radiance_dev && delta_dev && g_rgb_dev && g_sigma_dev && g_radiance_dev,
+                 "nerf_composite_bwd: null pointer");
+  NERF_CHECK_ARG(n >= 0 && s > 0 && s <= 2048, "nerf_composite_bwd: samples per ray must be in [1,2048]");
+  if (n == 0) return NERF_OK;
+  composite_bwd_kernel<<<(unsigned)ceil_div64(n, kCompWarps), kCompWarps * 32, 0, as_stream(stream)>>>(
+      sigma_dev, radiance_dev, delta_dev, g_rgb_dev, g_w_dev, n, s, g_sigma_dev, g_radiance_dev);
+  NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
+
+}  // extern "C"
