@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the per-ray rendering hot path (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--precision bf16|fp32]
+
+Metric: train rays/s, one training step = coarse (64) + fine (64+128) forward and backward of a 4096-ray batch
+per GPU on a lego-shaped synthetic scene (800x800 cameras, near/far 2/6), gradients all-reduced over NCCL, Adam
+step included (BASELINE.json configs[1]; weak scaling for N > 1 = configs[3] shape).  The same line also reports
+the 800x800 full-frame render latency (configs[2]) under "render".
+
+`--impl reference` times the reference's CPU path (the numpy oracle port, all host threads) on a bounded sample.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+SC, SF = 64, 128
+IMG = 800
+FLOP_FWD_PER_EVAL = 2 * 593408
+FLOP_TRAIN_PER_EVAL = 3489024
+METRIC = "train rays/s (64+128 samples, fwd+bwd); 800x800 render ms @1/2/4/8 B200"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "tf_burst": p["bf16_tflops"], "tf_sustained": p["bf16_tflops_sustained"], "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------ synthetic scene
+def pose_spherical(theta_deg, phi_deg, radius):
+    """Blender-shaped camera-to-world (reference utils/data/load_blender.py:78-109)."""
+    import torch
+
+    t = torch.eye(4)
+    t[2, 3] = radius
+    phi, th = phi_deg / 180.0 * math.pi, theta_deg / 180.0 * math.pi
+    rp = torch.tensor([[1, 0, 0, 0], [0, math.cos(phi), -math.sin(phi), 0], [0, math.sin(phi), math.cos(phi), 0], [0, 0, 0, 1.0]])
+    rt = torch.tensor([[math.cos(th), 0, -math.sin(th), 0], [0, 1, 0, 0], [math.sin(th), 0, math.cos(th), 0], [0, 0, 0, 1.0]])
+    flip = torch.tensor([[-1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1.0]])
+    return flip @ (rt @ (rp @ t))
+
+
+def blender_focal(w, angle=0.6911112070083618):
+    return 0.5 * w / math.tan(0.5 * angle)
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.samples, self._stop, self._th = gpu_index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._th = threading.Thread(target=self._run, daemon=True)
+        self._th.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._th.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline (oracle port)
+def cpu_train_step_rays_per_s(rays, reps, seed=0):
+    """Times the oracle's training iteration (train.py:130-218 restated in numpy) on the host cores."""
+    from oracle import nerf_oracle as orc
+
+    rng = np.random.default_rng(seed)
+    pc, pf = orc.init_nerf_params(seed=1), orc.init_nerf_params(seed=2)
+    focal = orc.blender_focal(IMG)
+    c2w = orc.pose_spherical(30.0, -30.0, 4.0)
+    coords = orc.screen_coords(IMG, IMG)[rng.choice(IMG * IMG, size=rays, replace=False)]
+    o, d = orc.generate_rays(coords, orc.make_intrinsic(focal, focal, IMG, IMG), c2w, 2.0, IMG, IMG, False)
+    target = rng.random((rays, 3), dtype=np.float32)
+    times = []
+    for _ in range(reps):
+        u = [rng.random((rays, k), dtype=np.float32) for k in (SC, SC, SF, SF)]
+        t0 = time.perf_counter()
+        orc.train_step_grads(pc, pf, o, d, 2.0, 6.0, SC, SF, target, *u)
+        times.append(time.perf_counter() - t0)
+    return rays / float(np.median(times)), float(np.median(times))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rays = 256
+    cores = os.cpu_count() or 1
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_train_step_rays_per_s(rays, 1)
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    rps, med = cpu_train_step_rays_per_s(rays, steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rps, "unit": "rays/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": 1, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"train step, {rays}-ray sample of the 4096-ray batch, 800x800 lego-shaped camera, 64+128 samples, CPU",
+                   "rays_per_step": rays},
+        "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} x {rays}-ray training iterations (oracle numpy port of the reference path, BLAS threads = all cores)"},
+        "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import torch_nerf_b200 as tn
+    from torch_nerf_b200.engine import HotPathEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n_rays = args.rays
+    torch.manual_seed(0)  # identical replicas of both networks on every rank
+    coarse = tn.NeRF(63, 27, precision=args.precision).to(dev)
+    fine = tn.NeRF(63, 27, precision=args.precision).to(dev)
+    eng = HotPathEngine(coarse, fine, SC, SF, precision=args.precision)
+    flat = eng.enable_flat_params()
+    eng_render = eng if args.precision == "bf16" else HotPathEngine(coarse, fine, SC, SF, precision="bf16")
+    params = [p for net in (coarse, fine) for p in net.ordered_parameters()]
+    # runner_utils.py:690-711: Adam(lr 5e-4, eps 1e-8), ExponentialLR gamma = (5e-5/5e-4)^(1/300000)
+    opt = torch.optim.Adam(params, lr=5e-4, eps=1e-8, fused=True)
+    sched = torch.optim.lr_scheduler.ExponentialLR(opt, (5e-5 / 5e-4) ** (1.0 / 300000))
+    torch.manual_seed(1234 + rank)  # per-rank uniform stream / pixels
+    focal = blender_focal(IMG)
+    poses = [pose_spherical(th, -30.0, 4.0) for th in np.linspace(-180, 180, 9)[:-1]]
+    cams = [tn.PerspectiveCamera({"f_x": focal, "f_y": focal, "img_width": IMG, "img_height": IMG}, p, 2.0, 6.0) for p in poses]
+    total_steps = args.steps + args.warmup
+    g = torch.Generator().manual_seed(99 + rank)
+    host_pix = [torch.randperm(IMG * IMG, generator=g)[:n_rays].contiguous().pin_memory() for _ in range(total_steps)]
+    host_tgt = [torch.rand((n_rays, 3), generator=g).pin_memory() for _ in range(total_steps)]
+    dev_pix = [p.to(dev) for p in host_pix]
+    dev_tgt = [t.to(dev) for t in host_tgt]
+    losses_host = torch.zeros((total_steps, 2)).pin_memory()
+    losses_dev = torch.zeros((2,), device=dev)
+    in_pix = torch.empty((n_rays,), device=dev, dtype=torch.int64)
+    in_tgt = torch.empty((n_rays, 3), device=dev)
+
+    def step(i, e2e):
+        cam = cams[i % len(cams)]
+        if e2e:
+            in_pix.copy_(host_pix[i], non_blocking=True)
+            in_tgt.copy_(host_tgt[i], non_blocking=True)
+            pix, tgt = in_pix, in_tgt
+        else:
+            pix, tgt = dev_pix[i], dev_tgt[i]
+        eng.train_pixels(cam, pix, tgt, False, loss_out=losses_dev)
+        if world > 1:
+            dist.all_reduce(flat.grad)
+            flat.grad.mul_(1.0 / world)
+        opt.step()
+        sched.step()
+        if e2e:
+            losses_host[i].copy_(losses_dev, non_blocking=True)
+
+    def timed(e2e):
+        for i in range(args.warmup):
+            step(i, e2e)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        l0 = eng.launches
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(args.warmup, total_steps):
+            step(i, e2e)
+        ev1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, eng.launches - l0
+
+    with ClockSampler(local) as clk:
+        ms_dev, launches = timed(False)
+        ms_e2e, _ = timed(True)
+    clocks = clk.summary()
+    rays_total = n_rays * world * args.steps
+    value = rays_total / (ms_dev * 1e-3)
+    e2e_value = rays_total / (ms_e2e * 1e-3)
+    pk = peaks()
+
+    # ---- roofline of the dominant kernel: the tensor-core forward chain on the fine pass's rows
+    roof = None
+    render = None
+    if rank == 0:
+        if True:
+            lib = tn._lib.load()
+            m = n_rays * (SC + SF)
+            ray_o = torch.randn(n_rays, 3, device=dev)
+            ray_d = torch.randn(n_rays, 3, device=dev)
+            t = torch.rand(n_rays, SC + SF, device=dev) * 4 + 2
+            sig = torch.empty(m, device=dev)
+            rgb = torch.empty(m, 3, device=dev)
+            packed = fine.packed_weights()
+            P = tn._lib.ptr
+
+            def k():
+                tn._lib.check(lib.nerf_mlp_bf16_forward(P(packed, torch.uint8), None, None, P(ray_o), P(ray_d), P(t), SC + SF, m,
+                                                        P(sig), P(rgb), None, tn._lib.stream()), "fwd")
+            for _ in range(3):
+                k()
+            reps = 10
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            ev0.record()
+            for _ in range(reps):
+                k()
+            ev1.record()
+            torch.cuda.synchronize()
+            sec = ev0.elapsed_time(ev1) * 1e-3 / reps
+            ach = m * FLOP_FWD_PER_EVAL / sec / 1e12
+            roof = {"bound": "tensor", "kernel": "mlp_fwd_kernel (tcgen05 forward chain, 786432 rows)", "achieved": ach,
+                    "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "traffic": None,
+                    "peak_source": pk["src"] + " (burst: kernel timed alone)", "launch_ms": sec * 1e3}
+        # ---- full 800x800 frame (configs[2])
+        cam = cams[0]
+        for _ in range(2):
+            eng_render.render_frame(cam)
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        ev0.record()
+        for _ in range(reps):
+            img = eng_render.render_frame(cam)
+        ev1.record()
+        torch.cuda.synchronize()
+        frame_ms = ev0.elapsed_time(ev1) / reps
+        flop_frame = IMG * IMG * (SC + SC + SF) * FLOP_FWD_PER_EVAL
+        render = {"frame_ms_1gpu": frame_ms, "resolution": [IMG, IMG], "rays_per_s": IMG * IMG / (frame_ms * 1e-3),
+                  "tensor_frac_sustained": flop_frame / (frame_ms * 1e-3) / 1e12 / pk["tf_sustained"],
+                  "finite": bool(torch.isfinite(img).all().item())}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            rps, med = cpu_train_step_rays_per_s(256, 3)
+            cpu = {"value": rps, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
+                   "sample": "3 x 256-ray training iterations of the oracle (numpy port of the reference CPU path), median"}
+        step_flop = n_rays * (SC + SC + SF) * FLOP_TRAIN_PER_EVAL
+        line = {
+            "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": "single training step (coarse 64 + fine 64+128, fwd+bwd, Adam), 4096-ray batch per GPU, "
+                                   "lego-shaped synthetic scene, 800x800 cameras, near/far 2/6",
+                       "rays_per_gpu": n_rays, "global_rays": n_rays * world, "samples": [SC, SF],
+                       "l2_policy": "per-step working set (activation cache + gradients, >1 GB) exceeds the 126 MB L2",
+                       "precision": args.precision},
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n_rays * 8 + n_rays * 12,
+                    "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clocks,
+            "step_tensor_frac_sustained": step_flop / (ms_dev / args.steps * 1e-3) / 1e12 / pk["tf_sustained"],
+            "roofline": roof, "cpu_baseline": cpu, "render": render,
+            "loss_last": [float(x) for x in losses_host[total_steps - 1]],
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("NERF_B200_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--rays", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        args.warmup = max(args.warmup, 3)
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -122,6 +122,11 @@ int nerf_composite_bwd(const float* sigma_dev, const float* radiance_dev, const 
                        const float* g_rgb_dev, const float* g_w_dev, int64_t n, int s, float* g_sigma_dev,
                        float* g_radiance_dev, nerf_stream_t stream);
 
+/* MSE loss head of one render pass (runners/runner_utils.py:731 nn.MSELoss as used at runners/train.py:180,202):
+ * *loss_accum_dev += mean((rgb - target)^2) over the N*3 elements; g_rgb = 2/(3N) (rgb - target). */
+int nerf_mse_loss(const float* rgb_dev, const float* target_dev, int64_t n, float* g_rgb_dev,
+                  float* loss_accum_dev, nerf_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K5 / K6 NeRF MLP
  *   replaces NeRF.forward (src/network/nerf.py:65-121) and its autograd backward.

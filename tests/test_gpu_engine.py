@@ -1,0 +1,110 @@
+"""GPU tests of the fused engine (torch-nerf_b200/engine.py): the same golden vectors as the drop-in classes,
+through the no-materialisation pipeline."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import check_digest, load_golden
+from oracle import nerf_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tn():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import torch_nerf_b200 as mod
+
+    mod._lib.load()
+    return mod
+
+
+def cu(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+def nets(tn, seed_c, seed_f, precision):
+    out = []
+    for seed in (seed_c, seed_f):
+        net = tn.NeRF(63, 27, precision=precision)
+        net.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in orc.init_nerf_params(seed=seed).items()})
+        out.append(net.cuda())
+    return out
+
+
+def camera(tn, g):
+    h, w, focal = int(g["h"]), int(g["w"]), float(g["focal"])
+    return tn.PerspectiveCamera({"f_x": focal, "f_y": focal, "img_width": w, "img_height": h}, torch.from_numpy(g["c2w"]), 2.0, 6.0)
+
+
+def test_engine_train_step_golden_fp32(tn):
+    from torch_nerf_b200.engine import HotPathEngine
+
+    g = load_golden("train_step.npz")
+    coarse, fine = nets(tn, int(g["seed_c"]), int(g["seed_f"]), "fp32")
+    eng = HotPathEngine(coarse, fine, 64, 128, precision="fp32")
+    losses = eng.train_pixels(camera(tn, g), cu(g["pix"]), cu(g["target"]), False,
+                              uniforms=(cu(g["u_c"]), cu(g["u0"]), cu(g["u1"]), cu(g["u2"])))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(eng.last["coarse"]["rgb"].cpu().numpy(), g["rgb_c"], rtol=0, atol=1e-3)
+    np.testing.assert_allclose(eng.last["fine"]["rgb"].cpu().numpy(), g["rgb_f"], rtol=0, atol=1e-3)
+    np.testing.assert_allclose(losses.cpu().numpy(), [float(g["loss_c"]), float(g["loss_f"])], rtol=1e-3)
+    check_digest({k: p.grad.cpu().numpy() for k, p in coarse.named_parameters()}, g, prefix="c/", rtol=5e-3, atol=1e-6)
+    check_digest({k: p.grad.cpu().numpy() for k, p in fine.named_parameters()}, g, prefix="f/", rtol=5e-3, atol=1e-6)
+    # the flat buffers alias the parameters and gradients
+    assert eng.flat.flat.numel() == 2 * 595844
+    assert coarse.fc_in.weight.data_ptr() == eng.flat.flat.data_ptr()
+    assert coarse.fc_in.weight.grad.data_ptr() == eng.flat.grad.data_ptr()
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 2e-2)])
+def test_engine_render_golden(tn, precision, tol):
+    from torch_nerf_b200.engine import HotPathEngine
+
+    g = load_golden("render.npz")
+    coarse, fine = nets(tn, int(g["seed_c"]), int(g["seed_f"]), precision)
+    eng = HotPathEngine(coarse, fine, 64, 128, precision=precision)
+    cam = camera(tn, g)
+    ray_o, ray_d, n = eng.rays_from_pixels(cam, False, None, 0, int(g["h"]) * int(g["w"]))
+    out = eng.render_rays(ray_o, ray_d, 2.0, 6.0, uniforms=(cu(g["u_c"]), cu(g["u0"]), cu(g["u1"]), cu(g["u2"])))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out["rgb_coarse"].cpu().numpy(), g["rgb_c"], rtol=0, atol=tol)
+    np.testing.assert_allclose(out["weights_coarse"].cpu().numpy(), g["w_c"] + (1e-5 if False else 0), rtol=0, atol=tol)
+    if precision == "fp32":
+        # fine-pass bin decisions were made from the engine's own coarse weights (1e-6 away from the reference's)
+        np.testing.assert_allclose(out["rgb_fine"].cpu().numpy(), g["rgb_f"], rtol=0, atol=tol)
+    else:
+        err = np.abs(out["rgb_fine"].cpu().numpy() - g["rgb_f"])
+        assert err.mean() < 2e-3
+    img = eng.render_frame(cam)
+    assert img.shape == (n, 3) and float(img.min()) >= 0.0 and float(img.max()) <= 1.0
+
+
+def test_engine_bf16_psnr_gate(tn):
+    """BF16 must stay within 0.1 dB PSNR of the fp32 path (north star): PSNR of each render against the same
+    synthetic ground-truth pixels."""
+    from torch_nerf_b200.engine import HotPathEngine
+
+    torch.manual_seed(7)
+    c32, f32 = nets(tn, 51, 52, "fp32")
+    c16, f16 = nets(tn, 51, 52, "bf16")
+    e32 = HotPathEngine(c32, f32, 64, 128, precision="fp32")
+    e16 = HotPathEngine(c16, f16, 64, 128, precision="bf16")
+    h = w = 64
+    focal = orc.blender_focal(w)
+    cam = tn.PerspectiveCamera({"f_x": focal, "f_y": focal, "img_width": w, "img_height": h},
+                               torch.from_numpy(orc.pose_spherical(45.0, -30.0, 4.0)), 2.0, 6.0)
+    n = h * w
+    u = (torch.rand(n, 64).cuda(), torch.rand(n, 64).cuda(), torch.rand(n, 128).cuda(), torch.rand(n, 128).cuda())
+    ray_o, ray_d, _ = e32.rays_from_pixels(cam, False, None, 0, n)
+    a = e32.render_rays(ray_o.clone(), ray_d.clone(), 2.0, 6.0, uniforms=u)["rgb_fine"].clone()
+    b = e16.render_rays(ray_o.clone(), ray_d.clone(), 2.0, 6.0, uniforms=u)["rgb_fine"].clone()
+    gt = torch.rand(n, 3, device="cuda")
+
+    def psnr(x):
+        return float(-10.0 * torch.log10(torch.mean((x.clamp(0, 1) - gt) ** 2)))
+
+    assert abs(psnr(a) - psnr(b)) < 0.1, (psnr(a), psnr(b))
+    direct = float(-10.0 * torch.log10(torch.mean((a - b) ** 2)))
+    assert direct > 35.0, direct  # bf16 image vs fp32 image

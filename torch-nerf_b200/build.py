@@ -34,8 +34,8 @@ def _digest():
     files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(ROOT, "include", "nerf_b200.h")]
     for f in files:
         with open(f, "rb") as fh:
-            h.update(f.encode() + b"\0" + fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+            h.update(os.path.basename(f).encode() + b"\0" + fh.read())
+    h.update(" ".join(a for a in NVCC_FLAGS if not a.startswith("-I")).encode())
     return h.hexdigest()
 
 

@@ -254,6 +254,7 @@ extern "C" {
 
 int nerf_posenc(const float* x_dev, int64_t m, int in_dim, int embed_level, int include_input, float* out_dev,
                 int64_t ld_out, nerf_stream_t stream) {
+  if (m == 0) return NERF_OK;
   NERF_CHECK_ARG(x_dev && out_dev, "nerf_posenc: null pointer");
   NERF_CHECK_ARG(m >= 0 && in_dim > 0 && embed_level >= 0 && embed_level <= 32, "nerf_posenc: bad sizes");
   const int out_dim = in_dim * (2 * embed_level + (include_input ? 1 : 0));
@@ -272,8 +273,9 @@ int nerf_posenc(const float* x_dev, int64_t m, int in_dim, int embed_level, int 
 int nerf_composite_fwd(const float* sigma_dev, const float* radiance_dev, const float* delta_dev,
                        const float* t_dev, int64_t n, int s, float* rgb_dev, float* w_dev, float* depth_dev,
                        float* opacity_dev, nerf_stream_t stream) {
-  NERF_CHECK_ARG(sigma_dev && radiance_dev && delta_dev && rgb_dev, "nerf_composite_fwd: null pointer");
   NERF_CHECK_ARG(n >= 0 && s > 0, "nerf_composite_fwd: bad sizes");
+  if (n == 0) return NERF_OK;
+  NERF_CHECK_ARG(sigma_dev && radiance_dev && delta_dev && rgb_dev, "nerf_composite_fwd: null pointer");
   NERF_CHECK_ARG(depth_dev == nullptr || t_dev != nullptr, "nerf_composite_fwd: depth needs t");
   if (n == 0) return NERF_OK;
   composite_fwd_kernel<<<(unsigned)ceil_div64(n, kCompWarps), kCompWarps * 32, 0, as_stream(stream)>>>(
@@ -285,9 +287,10 @@ int nerf_composite_fwd(const float* sigma_dev, const float* radiance_dev, const 
 int nerf_composite_bwd(const float* sigma_dev, const float* radiance_dev, const float* delta_dev,
                        const float* g_rgb_dev, const float* g_w_dev, int64_t n, int s, float* g_sigma_dev,
                        float* g_radiance_dev, nerf_stream_t stream) {
+  NERF_CHECK_ARG(n >= 0 && s > 0 && s <= 2048, "nerf_composite_bwd: samples per ray must be in [1,2048]");
+  if (n == 0) return NERF_OK;
   NERF_CHECK_ARG(sigma_dev && radiance_dev && delta_dev && g_rgb_dev && g_sigma_dev && g_radiance_dev,
                  "nerf_composite_bwd: null pointer");
-  NERF_CHECK_ARG(n >= 0 && s > 0 && s <= 2048, "nerf_composite_bwd: samples per ray must be in [1,2048]");
   if (n == 0) return NERF_OK;
   composite_bwd_kernel<<<(unsigned)ceil_div64(n, kCompWarps), kCompWarps * 32, 0, as_stream(stream)>>>(
       sigma_dev, radiance_dev, delta_dev, g_rgb_dev, g_w_dev, n, s, g_sigma_dev, g_radiance_dev);
@@ -296,3 +299,43 @@ int nerf_composite_bwd(const float* sigma_dev, const float* radiance_dev, const 
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// MSE loss head of the training step (runner_utils.py:731 nn.MSELoss, train.py:180/202):
+//   loss += mean((rgb - target)^2) over N*3 elements;  g_rgb = 2/(3N) * (rgb - target)
+// ------------------------------------------------------------------------------------------------
+namespace nerf {
+__global__ void __launch_bounds__(256) mse_kernel(const float* __restrict__ rgb, const float* __restrict__ target,
+                                                  int64_t cnt, float inv_cnt, float* __restrict__ g_rgb,
+                                                  float* __restrict__ loss_accum) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float sq = 0.f;
+  if (e < cnt) {
+    float d = rgb[e] - target[e];
+    g_rgb[e] = 2.0f * inv_cnt * d;
+    sq = d * d;
+  }
+  sq = warp_sum(sq);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i];
+    atomicAdd(loss_accum, t * inv_cnt);
+  }
+}
+}  // namespace nerf
+
+extern "C" int nerf_mse_loss(const float* rgb_dev, const float* target_dev, int64_t n, float* g_rgb_dev,
+                             float* loss_accum_dev, nerf_stream_t stream) {
+  NERF_CHECK_ARG(n >= 0, "nerf_mse_loss: negative ray count");
+  if (n == 0) return NERF_OK;
+  NERF_CHECK_ARG(rgb_dev && target_dev && g_rgb_dev && loss_accum_dev, "nerf_mse_loss: null pointer");
+  const int64_t cnt = 3 * n;
+  nerf::mse_kernel<<<(unsigned)nerf::ceil_div64(cnt, 256), 256, 0, nerf::as_stream(stream)>>>(
+      rgb_dev, target_dev, cnt, 1.0f / (float)cnt, g_rgb_dev, loss_accum_dev);
+  NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}

@@ -31,7 +31,6 @@ constexpr int kTileM = 128;
 constexpr int kNumTcLayers = 10;  // fc_in, fc_1..fc_7, fc_8(feat), fc_9
 __host__ __device__ constexpr int layer_nk(int l) { return l == 0 ? 1 : ((l == 5 || l == 9) ? 5 : 4); }
 __host__ __device__ constexpr int layer_n(int l) { return l == 9 ? kH : kF; }
-constexpr int kFwdChunks = 1 + 4 * 4 + 5 + 3 * 4 + 5;  // 39
 constexpr size_t kFwdWeightBytes = (size_t)(1 + 16 + 5 + 12) * 32768 + 5 * 16384;
 
 // fp32 constants block appended to the packed weights (float offsets)

@@ -305,9 +305,9 @@ extern "C" {
 
 int nerf_generate_rays(const int64_t* coords_dev, int64_t n, const nerf_camera_t* cam, float* ray_o_dev,
                        float* ray_d_dev, nerf_stream_t stream) {
-  NERF_CHECK_ARG(cam && coords_dev && ray_o_dev && ray_d_dev, "nerf_generate_rays: null pointer");
   NERF_CHECK_ARG(n >= 0, "nerf_generate_rays: negative ray count");
   if (n == 0) return NERF_OK;
+  NERF_CHECK_ARG(cam && coords_dev && ray_o_dev && ray_d_dev, "nerf_generate_rays: null pointer");
   raygen_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, as_stream(stream)>>>(coords_dev, nullptr, 0, n, *cam,
                                                                              ray_o_dev, ray_d_dev);
   NERF_LAUNCH_CHECK();
@@ -317,9 +317,10 @@ int nerf_generate_rays(const int64_t* coords_dev, int64_t n, const nerf_camera_t
 int nerf_generate_rays_from_pixels(const int64_t* pixel_idx_dev, int64_t first_pixel, int64_t n,
                                    const nerf_camera_t* cam, float* ray_o_dev, float* ray_d_dev,
                                    nerf_stream_t stream) {
-  NERF_CHECK_ARG(cam && ray_o_dev && ray_d_dev, "nerf_generate_rays_from_pixels: null pointer");
-  NERF_CHECK_ARG(n >= 0 && cam->img_w > 0 && cam->img_h > 0, "nerf_generate_rays_from_pixels: bad sizes");
+  NERF_CHECK_ARG(n >= 0, "nerf_generate_rays_from_pixels: negative ray count");
   if (n == 0) return NERF_OK;
+  NERF_CHECK_ARG(cam && ray_o_dev && ray_d_dev, "nerf_generate_rays_from_pixels: null pointer");
+  NERF_CHECK_ARG(cam->img_w > 0 && cam->img_h > 0, "nerf_generate_rays_from_pixels: bad image size");
   raygen_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, as_stream(stream)>>>(nullptr, pixel_idx_dev, first_pixel, n,
                                                                              *cam, ray_o_dev, ray_d_dev);
   NERF_LAUNCH_CHECK();
@@ -345,10 +346,10 @@ int nerf_make_bins(double t_near, double t_far, int num_partitions, float* bins_
 int nerf_sample_coarse(const float* ray_o_dev, const float* ray_d_dev, int64_t n, int num_samples, double t_near,
                        double t_far, const float* u_dev, float* t_dev, float* pts_dev, float* dirs_dev,
                        float* delta_dev, nerf_stream_t stream) {
-  NERF_CHECK_ARG(ray_o_dev && ray_d_dev && u_dev, "nerf_sample_coarse: null pointer");
   NERF_CHECK_ARG(num_samples > 0 && num_samples <= 1024, "nerf_sample_coarse: num_samples must be in [1,1024]");
   NERF_CHECK_ARG(n >= 0, "nerf_sample_coarse: negative ray count");
-  if (n == 0) return NERF_OK;
+  if (n == 0) return NERF_OK;  // empty ray set: nothing to do (zero-size tensors have null data pointers)
+  NERF_CHECK_ARG(ray_o_dev && ray_d_dev && u_dev, "nerf_sample_coarse: null pointer");
   size_t smem = sizeof(float) * kWarpsPerBlock * (num_samples + 96);
   sample_coarse_kernel<<<(unsigned)ceil_div64(n, kWarpsPerBlock), kWarpsPerBlock * 32, smem, as_stream(stream)>>>(
       ray_o_dev, ray_d_dev, n, num_samples, make_bin_spec(t_near, t_far, num_samples), u_dev, t_dev, pts_dev, dirs_dev,
@@ -360,10 +361,10 @@ int nerf_sample_coarse(const float* ray_o_dev, const float* ray_d_dev, int64_t n
 int nerf_sample_pdf(double t_near, double t_far, float* weights_dev, const float* u1_dev, const float* u2_dev,
                     int64_t n, int num_coarse, int num_fine, float* t_fine_dev, int64_t* idx_dev,
                     nerf_stream_t stream) {
-  NERF_CHECK_ARG(weights_dev && u1_dev && u2_dev && t_fine_dev, "nerf_sample_pdf: null pointer");
   NERF_CHECK_ARG(num_coarse > 0 && num_coarse <= 1024 && num_fine > 0, "nerf_sample_pdf: bad sample counts");
   NERF_CHECK_ARG(n >= 0, "nerf_sample_pdf: negative ray count");
   if (n == 0) return NERF_OK;
+  NERF_CHECK_ARG(weights_dev && u1_dev && u2_dev && t_fine_dev, "nerf_sample_pdf: null pointer");
   size_t smem = sizeof(float) * kWarpsPerBlock * 2 * num_coarse;
   sample_pdf_kernel<<<(unsigned)ceil_div64(n, kWarpsPerBlock), kWarpsPerBlock * 32, smem, as_stream(stream)>>>(
       make_bin_spec(t_near, t_far, num_coarse), weights_dev, u1_dev, u2_dev, n, num_coarse, num_fine, t_fine_dev,
@@ -376,12 +377,12 @@ int nerf_sample_fine(const float* ray_o_dev, const float* ray_d_dev, int64_t n, 
                      double t_near, double t_far, float* weights_dev, const float* u0_dev, const float* u1_dev,
                      const float* u2_dev, int64_t* idx_dev, float* t_dev, float* pts_dev, float* dirs_dev,
                      float* delta_dev, nerf_stream_t stream) {
-  NERF_CHECK_ARG(ray_o_dev && ray_d_dev && weights_dev && u0_dev && u1_dev && u2_dev,
-                 "nerf_sample_fine: null pointer");
   NERF_CHECK_ARG(num_coarse > 0 && num_fine > 0 && num_coarse + num_fine <= 2048,
                  "nerf_sample_fine: num_coarse + num_fine must be <= 2048");
   NERF_CHECK_ARG(n >= 0, "nerf_sample_fine: negative ray count");
   if (n == 0) return NERF_OK;
+  NERF_CHECK_ARG(ray_o_dev && ray_d_dev && weights_dev && u0_dev && u1_dev && u2_dev,
+                 "nerf_sample_fine: null pointer");
   const int p2 = next_pow2(num_coarse + num_fine);
   size_t smem = sizeof(float) * kWarpsPerBlock * (p2 + 2 * num_coarse + 96);
   if (smem > 48 * 1024) {

@@ -1,0 +1,232 @@
+"""Fused hot-path engine: the coarse -> fine render pass and the training step (forward + backward) driven as one
+stream of libnerf_b200 kernels with no host synchronisation and no (N,S,3) materialisation.
+
+This is the fast caller of the same C-ABI the drop-in classes use.  It restates what the reference's callers do
+around `VolumeRenderer.render_scene`:
+  * training iteration  -- runners/train.py:130-218 (coarse render, MSE, fine render from the coarse weights, MSE,
+                           backward; optimizer step stays with the caller)
+  * full-frame render   -- runners/render.py:58-107 (coarse + fine over all H*W pixels, clamp to [0,1])
+Uniform draws follow the reference's order and shapes (1 draw for the coarse pass, 3 for the fine pass).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from .cameras import PerspectiveCamera
+from .network import NeRF
+
+
+class FlatParams:
+    """Re-homes the parameters of the coarse and fine networks into ONE flat fp32 buffer (and one flat gradient
+    buffer), so the data-parallel exchange is a single all-reduce over 2 x 595 844 floats and the kernels write
+    gradients straight into it."""
+
+    def __init__(self, nets: Sequence[NeRF]):
+        self.nets = list(nets)
+        params = [p for net in self.nets for p in net.ordered_parameters()]
+        dev = params[0].device
+        total = sum(p.numel() for p in params)
+        self.flat = torch.empty(total, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        off = 0
+        self.grad_views = []
+        for p in params:
+            n = p.numel()
+            self.flat[off:off + n].copy_(p.detach().reshape(-1))
+            p.data = self.flat[off:off + n].view_as(p)
+            g = self.grad[off:off + n].view_as(p)
+            p.grad = g
+            self.grad_views.append(g)
+            off += n
+        self.per_net = len(params) // len(self.nets)
+
+    def grads_of(self, i: int):
+        return self.grad_views[i * self.per_net:(i + 1) * self.per_net]
+
+
+class HotPathEngine:
+    def __init__(self, coarse: NeRF, fine: NeRF, num_coarse: int = 64, num_fine: int = 128, precision: str = "bf16"):
+        self.lib = _lib.load()
+        self.nets = (coarse, fine)
+        self.sc, self.sf = int(num_coarse), int(num_fine)
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        if precision == "bf16" and not (coarse.supports_bf16() and fine.supports_bf16()):
+            raise ValueError("the bf16 tensor-core chain is built for NeRF(63, 27, 256)")
+        self.precision = precision
+        self.device = next(coarse.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("HotPathEngine needs CUDA parameters (no CPU fallback)")
+        self.flat: Optional[FlatParams] = None
+        self._buf: Dict[Tuple, torch.Tensor] = {}
+        self.launches = 0  # kernels of this library enqueued so far (host-side count)
+
+    # ------------------------------------------------------------------------------------------ buffers
+    def _get(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
+        key = (name, tuple(shape), dtype)
+        t = self._buf.get(key)
+        if t is None:
+            t = torch.empty(shape, device=self.device, dtype=dtype)
+            self._buf[key] = t
+        return t
+
+    def _call(self, fn_name: str, *args, launches: int = 1):
+        _lib.check(getattr(self.lib, fn_name)(*args), fn_name)
+        self.launches += launches
+
+    def enable_flat_params(self) -> FlatParams:
+        if self.flat is None:
+            self.flat = FlatParams(self.nets)
+        return self.flat
+
+    # ------------------------------------------------------------------------------------------ pieces
+    def _uniforms(self, n: int, uniforms, fine: bool):
+        if uniforms is not None:
+            return [u.to(self.device, torch.float32).contiguous() for u in uniforms]
+        if fine:
+            return [torch.rand((n, self.sc), device=self.device), torch.rand((n, self.sf), device=self.device),
+                    torch.rand((n, self.sf), device=self.device)]
+        return [torch.rand((n, self.sc), device=self.device)]
+
+    def _sample(self, tag, ray_o, ray_d, n, near, far, weights, u, need_points: bool):
+        P, st = _lib.ptr, _lib.stream()
+        s = self.sc + self.sf if weights is not None else self.sc
+        t = self._get(tag + "t", (n, s))
+        delta = self._get(tag + "delta", (n, s))
+        pts = self._get(tag + "pts", (n, s, 3)) if need_points else None
+        dirs = self._get(tag + "dirs", (n, s, 3)) if need_points else None
+        if weights is None:
+            self._call("nerf_sample_coarse", P(ray_o), P(ray_d), n, self.sc, near, far, P(u[0]), P(t), P(pts), P(dirs),
+                       P(delta), st)
+        else:
+            self._call("nerf_sample_fine", P(ray_o), P(ray_d), n, self.sc, self.sf, near, far, P(weights), P(u[0]), P(u[1]),
+                       P(u[2]), None, P(t), P(pts), P(dirs), P(delta), st)
+        return t, delta, pts, dirs, s
+
+    def _pass(self, which: int, tag: str, ray_o, ray_d, n, near, far, weights, u, train: bool):
+        """One render pass (coarse: which=0, fine: which=1): sample -> query -> composite."""
+        P, st = _lib.ptr, _lib.stream()
+        net = self.nets[which]
+        fp32 = self.precision == "fp32"
+        t, delta, pts, dirs, s = self._sample(tag, ray_o, ray_d, n, near, far, weights, u, need_points=fp32)
+        m = n * s
+        sigma = self._get(tag + "sigma", (n, s))
+        rad = self._get(tag + "rad", (n, s, 3))
+        ctx = {"t": t, "delta": delta, "sigma": sigma, "rad": rad, "s": s, "m": m}
+        if fp32:
+            pe = self._get(tag + "pe", (m, net.pos_dim))
+            de = self._get(tag + "de", (m, net.view_dir_dim))
+            lp = (net.pos_dim - 3) // 6
+            lv = (net.view_dir_dim - 3) // 6
+            self._call("nerf_posenc", P(pts), m, 3, lp, 1, P(pe), net.pos_dim, st)
+            self._call("nerf_posenc", P(dirs), m, 3, lv, 1, P(de), net.view_dir_dim, st)
+            cache = self._get(tag + "cache", (self.lib.nerf_mlp_f32_cache_floats(net._dims, m),))
+            params = _lib.pointer_array([p.detach() for p in net.ordered_parameters()])
+            self._call("nerf_mlp_f32_forward", net._dims, params, P(pe), P(de), m, P(sigma), P(rad), P(cache), st, launches=16)
+            ctx["cache"] = cache
+        else:
+            packed = net.packed_weights()
+            cache = None
+            if train:
+                cache = self._get(tag + "cache16", (self.lib.nerf_mlp_bf16_cache_bytes(m),), torch.uint8)
+                ctx["cache"] = cache
+            self._call("nerf_mlp_bf16_forward", P(packed, torch.uint8), None, None, P(ray_o), P(ray_d), P(t), s, m, P(sigma),
+                       P(rad), P(cache, torch.uint8) if cache is not None else None, st)
+        rgb = self._get(tag + "rgb", (n, 3))
+        w = self._get(tag + "w", (n, s))
+        self._call("nerf_composite_fwd", P(sigma), P(rad), P(delta), None, n, s, P(rgb), P(w), None, None, st)
+        ctx["rgb"], ctx["w"] = rgb, w
+        return ctx
+
+    def _backward(self, which: int, ctx, n: int, g_rgb, grads):
+        P, st = _lib.ptr, _lib.stream()
+        net = self.nets[which]
+        s, m = ctx["s"], ctx["m"]
+        tag = "bc" if which == 0 else "bf"
+        g_sigma = self._get(tag + "gs", (n, s))
+        g_rad = self._get(tag + "gr", (n, s, 3))
+        self._call("nerf_composite_bwd", P(ctx["sigma"]), P(ctx["rad"]), P(ctx["delta"]), P(g_rgb), None, n, s, P(g_sigma),
+                   P(g_rad), st)
+        garr = _lib.pointer_array(grads)
+        if self.precision == "fp32":
+            scratch = self._get("scratch32", (self.lib.nerf_mlp_f32_bwd_scratch_floats(net._dims, n * (self.sc + self.sf)),))
+            params = _lib.pointer_array([p.detach() for p in net.ordered_parameters()])
+            self._call("nerf_mlp_f32_backward", net._dims, params, P(ctx["cache"]), P(ctx["rad"]), m, P(g_sigma), P(g_rad),
+                       garr, P(scratch), st, launches=60)
+        else:
+            scratch = self._get("scratch16", (self.lib.nerf_mlp_bf16_bwd_scratch_bytes(n * (self.sc + self.sf)),), torch.uint8)
+            self._call("nerf_mlp_bf16_backward", P(net.packed_weights(), torch.uint8), P(ctx["cache"], torch.uint8),
+                       P(ctx["rad"]), m, P(g_sigma), P(g_rad), garr, P(scratch, torch.uint8), st, launches=4)
+
+    # ------------------------------------------------------------------------------------------ public
+    def rays_from_pixels(self, camera: PerspectiveCamera, project_to_ndc: bool, pixel_indices: Optional[torch.Tensor],
+                         first_pixel: int = 0, count: int = 0):
+        P, st = _lib.ptr, _lib.stream()
+        n = int(pixel_indices.shape[0]) if pixel_indices is not None else int(count)
+        ray_o = self._get("ray_o", (n, 3))
+        ray_d = self._get("ray_d", (n, 3))
+        cam = camera.pack(project_to_ndc)
+        self._call("nerf_generate_rays_from_pixels", P(pixel_indices, torch.int64), int(first_pixel), n, cam, P(ray_o),
+                   P(ray_d), st)
+        return ray_o, ray_d, n
+
+    @torch.no_grad()
+    def render_rays(self, ray_o, ray_d, near: float, far: float, uniforms=None):
+        """Coarse + fine forward for given rays.  uniforms = (u_c, u0, u1, u2) or None."""
+        n = ray_o.shape[0]
+        with torch.cuda.device(self.device):
+            uc = self._uniforms(n, None if uniforms is None else uniforms[:1], fine=False)
+            co = self._pass(0, "c", ray_o, ray_d, n, float(near), float(far), None, uc, train=False)
+            uf = self._uniforms(n, None if uniforms is None else uniforms[1:], fine=True)
+            fi = self._pass(1, "f", ray_o, ray_d, n, float(near), float(far), co["w"], uf, train=False)
+        return {"rgb_coarse": co["rgb"], "weights_coarse": co["w"], "rgb_fine": fi["rgb"], "weights_fine": fi["w"],
+                "t_fine": fi["t"]}
+
+    @torch.no_grad()
+    def render_frame(self, camera: PerspectiveCamera, project_to_ndc: bool = False, first_pixel: int = 0,
+                     count: Optional[int] = None) -> torch.Tensor:
+        """runners/render.py:58-107: all (or a contiguous range of) pixels, coarse then fine, clamped to [0,1].
+        Returns (count, 3); reshape to (H, W, 3) for a full frame."""
+        total = camera.img_height * camera.img_width
+        count = total - first_pixel if count is None else count
+        with torch.cuda.device(self.device):
+            ray_o, ray_d, n = self.rays_from_pixels(camera, project_to_ndc, None, first_pixel, count)
+            out = self.render_rays(ray_o, ray_d, camera.t_near, camera.t_far)
+        return out["rgb_fine"].clamp(0.0, 1.0)
+
+    def train_rays(self, ray_o, ray_d, near: float, far: float, target: torch.Tensor, uniforms=None,
+                   loss_out: Optional[torch.Tensor] = None):
+        """Forward + backward of one training iteration (train.py:172-215) on given rays.  Gradients of both
+        networks are OVERWRITTEN in the flat gradient buffer; returns the device tensor [coarse_loss, fine_loss]."""
+        P, st = _lib.ptr, _lib.stream()
+        flat = self.enable_flat_params()
+        n = ray_o.shape[0]
+        near, far = float(near), float(far)
+        with torch.cuda.device(self.device), torch.no_grad():
+            losses = loss_out if loss_out is not None else self._get("losses", (2,))
+            losses.zero_()
+            uc = self._uniforms(n, None if uniforms is None else uniforms[:1], fine=False)
+            co = self._pass(0, "c", ray_o, ray_d, n, near, far, None, uc, train=True)
+            g_c = self._get("g_rgb_c", (n, 3))
+            self._call("nerf_mse_loss", P(co["rgb"]), P(target), n, P(g_c), P(losses[0:1]), st)
+            # the fine pass perturbs its copy of the coarse weights in place (utils.py:31)
+            w_pdf = self._get("w_pdf", (n, self.sc))
+            w_pdf.copy_(co["w"])
+            uf = self._uniforms(n, None if uniforms is None else uniforms[1:], fine=True)
+            fi = self._pass(1, "f", ray_o, ray_d, n, near, far, w_pdf, uf, train=True)
+            g_f = self._get("g_rgb_f", (n, 3))
+            self._call("nerf_mse_loss", P(fi["rgb"]), P(target), n, P(g_f), P(losses[1:2]), st)
+            # autograd order: the fine pass is differentiated first (train.py:190-215)
+            self._backward(1, fi, n, g_f, flat.grads_of(1))
+            self._backward(0, co, n, g_c, flat.grads_of(0))
+        self.last = {"coarse": co, "fine": fi}
+        return losses
+
+    def train_pixels(self, camera: PerspectiveCamera, pixel_indices: torch.Tensor, target: torch.Tensor,
+                     project_to_ndc: bool = False, uniforms=None, loss_out=None):
+        with torch.cuda.device(self.device):
+            ray_o, ray_d, n = self.rays_from_pixels(camera, project_to_ndc, pixel_indices)
+        return self.train_rays(ray_o, ray_d, camera.t_near, camera.t_far, target, uniforms, loss_out)
