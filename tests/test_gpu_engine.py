@@ -108,3 +108,26 @@ def test_engine_bf16_psnr_gate(tn):
     assert abs(psnr(a) - psnr(b)) < 0.1, (psnr(a), psnr(b))
     direct = float(-10.0 * torch.log10(torch.mean((a - b) ** 2)))
     assert direct > 35.0, direct  # bf16 image vs fp32 image
+
+
+def test_engine_train_step_bf16_vs_golden(tn):
+    """The tensor-core training step against the reference's fp32 gradients (bf16 accuracy)."""
+    from torch_nerf_b200.engine import HotPathEngine
+
+    g = load_golden("train_step.npz")
+    coarse, fine = nets(tn, int(g["seed_c"]), int(g["seed_f"]), "bf16")
+    eng = HotPathEngine(coarse, fine, 64, 128, precision="bf16")
+    losses = eng.train_pixels(camera(tn, g), cu(g["pix"]), cu(g["target"]), False,
+                              uniforms=(cu(g["u_c"]), cu(g["u0"]), cu(g["u1"]), cu(g["u2"])))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(eng.last["coarse"]["rgb"].cpu().numpy(), g["rgb_c"], rtol=0, atol=2e-2)
+    np.testing.assert_allclose(losses.cpu().numpy(), [float(g["loss_c"]), float(g["loss_f"])], rtol=2e-2)
+    for prefix, net in (("c/", coarse), ("f/", fine)):
+        for k, p in net.named_parameters():
+            got = p.grad.cpu().numpy().reshape(-1)
+            assert np.isfinite(got).all()
+            pos, val = g[f"{prefix}{k}/pos"], g[f"{prefix}{k}/val"]
+            scale = float(g[f"{prefix}{k}/abssum"]) / got.size
+            # sampled entries: bf16-level agreement relative to the tensor's mean magnitude
+            assert np.abs(got[pos] - val).max() < 0.25 * scale + 1e-7, (prefix, k)
+            np.testing.assert_allclose(np.abs(got.astype(np.float64)).sum(), float(g[f"{prefix}{k}/abssum"]), rtol=5e-2)

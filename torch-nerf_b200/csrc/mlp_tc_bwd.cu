@@ -1,0 +1,656 @@
+// K6 on the sm_100a tensor cores: backward of the NeRF MLP (autograd of network/nerf.py:102-119) in three kernels.
+//
+//  1. mlp_dgrad_kernel  -- the activation-gradient chain, same structure as the forward chain: per 128-row tile
+//        G9 = (g_rgb * rgb(1-rgb)) . W_out  masked by h9>0          (CUDA cores, 3 -> 128)
+//        j = 0: G8feat = G9 . W9[:, :256]                           (tcgen05, weights = transposed chunks)
+//        j = 1: G7 = (G8feat . W8[1:, :] + g_sigma_pre (x) W8[0, :]) masked by h7>0
+//        j = 2..8: G6 .. G0                                          (fc_5 uses only its h4 columns)
+//     every G is written to the backward scratch as a tile image for wgrad; ReLU masks come from the bit words
+//     the forward pass saved.  gz (M,3) and g_sigma_pre (M) are written as fp32 for the head kernel.
+//  2. mlp_wgrad_kernel  -- dW_l = G_l^T . X_l as split-K tcgen05 GEMMs over the saved tile images, both operands
+//     MN-major (rows = reduction index); a persistent CTA streams 32-row slices through a 5-stage bulk-copy ring,
+//     keeps a (2 x 128) x N fp32 accumulator in TMEM and flushes it with fp32 atomics at segment boundaries;
+//     bias gradients are column sums of the G slices taken from shared memory by otherwise idle warps.
+//  3. mlp_head_wgrad_kernel -- the two fp32 heads (fc_out, and row 0 of fc_8 = density) on CUDA cores.
+//
+// HBM-bound by design: wgrad must read G and X (2 x 512 B per row and layer); the chain kernels are tensor-bound.
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "mlp_tc_layout.cuh"
+#include "tc_common.cuh"
+
+namespace nerf {
+using namespace tc;
+
+// ================================================================================================
+// 1. dgrad chain
+// ================================================================================================
+constexpr int kDgStages = 4;
+constexpr int kDgStageBytes = 32768;
+constexpr int kDgThreads = 320;
+constexpr int kDgEpiThreads = 256;
+constexpr int kDgSmA = 0;
+constexpr int kDgSmW = 65536;
+constexpr int kDgSmC = kDgSmW + kDgStages * kDgStageBytes;  // w8row0 (256) | wout (384)
+constexpr int kDgSmBar = kDgSmC + 640 * 4;
+constexpr int kDgSmTotal = kDgSmBar + 256;
+constexpr int kDgSmemBytes = kDgSmTotal + 1024;
+
+struct DgradArgs {
+  const uint8_t* packed;
+  const uint8_t* cache;   // training cache (masks are read)
+  const float* rgb;       // (M,3) forward output
+  const float* g_sigma;   // (M)
+  const float* g_rgb;     // (M,3)
+  uint8_t* scratch;       // gradient tile images + gz + g_sigma_pre
+  int64_t m;
+};
+
+__device__ __forceinline__ void masked_group(const uint32_t (&v)[32], uint32_t mask, float add_scale,
+                                             const float* __restrict__ add_vec, float (&f)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    float t = __uint_as_float(v[i]);
+    if (add_vec != nullptr) t = fmaf(add_scale, add_vec[i], t);
+    f[i] = ((mask >> i) & 1u) ? t : 0.f;
+  }
+}
+
+__device__ __forceinline__ void store_group_bf16(const float (&f)[32], uint8_t* blk_row, int row, int chunk0) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 qv = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                          pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+    *reinterpret_cast<uint4*>(blk_row + (((chunk0 + j) ^ (row & 7)) << 4)) = qv;
+  }
+}
+
+__global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem + kDgSmA;
+  uint8_t* sW = smem + kDgSmW;
+  float* sC = reinterpret_cast<float*>(smem + kDgSmC);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDgSmBar);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kDgStages;
+  uint64_t* a_ready = bars + 2 * kDgStages;  // [4]
+  uint64_t* acc_full = a_ready + 4;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ntiles = num_tiles(a.m);
+  {
+    const float* cg = reinterpret_cast<const float*>(a.packed + kPackedConstOff);
+    for (int i = threadIdx.x; i < 640; i += kDgThreads) sC[i] = __ldg(cg + kCW8Row0 + i);  // w8row0 then wout (contiguous)
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kDgStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], 128);
+    mbar_init(&acc_full[0], 1);
+    mbar_init(&acc_full[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const float* sW8 = sC;         // fc_8.weight[0, :]
+  const float* sWout = sC + 256;  // fc_out.weight (3,128)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint8_t* src = a.packed + kPackedBwdOff;
+        for (int c = 0; c < kBwdChunks; ++c) {
+          const uint32_t s = g % kDgStages, ph = (g / kDgStages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], kDgStageBytes);
+          bulk_g2s(sW + s * kDgStageBytes, src, kDgStageBytes, &full[s]);
+          src += kDgStageBytes;
+          ++g;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t g = 0;
+      uint32_t a_cnt[4] = {0, 0, 0, 0};
+      constexpr uint32_t idesc = make_idesc_bf16(256, false, false);
+      const uint32_t sA_u = smem_u32(sA), sW_u = smem_u32(sW);
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int j = 0; j < kNumBwdLayers; ++j) {
+          const uint32_t acc = tmem_base + (uint32_t)(j & 1) * 256u;
+          const int nk = bwd_nk(j);
+          if (j == 0) {
+            // both column halves must have left the previous tile's last epilogue (they read accumulator 0, which
+            // this layer overwrites) -- each half signals its G9 block only after that
+            mbar_wait(&a_ready[0], a_cnt[0] & 1);
+            mbar_wait(&a_ready[1], a_cnt[1] & 1);
+            ++a_cnt[0];
+            ++a_cnt[1];
+          }
+#pragma unroll 1
+          for (int kb = 0; kb < nk; ++kb) {
+            if (j > 0) {
+              mbar_wait(&a_ready[kb], a_cnt[kb] & 1);
+              ++a_cnt[kb];
+            }
+            const uint32_t s = g % kDgStages, ph = (g / kDgStages) & 1;
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint64_t da = desc_kmajor(sA_u + kb * kBlockBytes);
+            const uint64_t db = desc_kmajor(sW_u + s * kDgStageBytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&empty[s]);
+            ++g;
+          }
+          umma_commit(&acc_full[j & 1]);
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t accn0 = 0, accn1 = 0;
+    uint8_t* a_row = sA + row * 128;
+    float* gz_out = reinterpret_cast<float*>(a.scratch + scratch_gz_offset(a.m));
+    float* gsp_out = reinterpret_cast<float*>(a.scratch + scratch_gsp_offset(a.m));
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t grow = tile * kTileM + row;
+      uint8_t* g_tile = a.scratch + (size_t)tile * kGradTileBytes;
+      const uint32_t* mask_tile =
+          reinterpret_cast<const uint32_t*>(a.cache + cache_mask_offset(a.m) + (size_t)tile * kMaskTileBytes);
+      // ---- heads on CUDA cores: gz = g_rgb * rgb (1 - rgb) (sigmoid backward), g_sigma_pre = g_sigma * (sigma_pre > 0)
+      float gz0 = 0.f, gz1 = 0.f, gz2 = 0.f, gsp = 0.f;
+      if (grow < a.m) {
+        const float r0 = __ldg(a.rgb + 3 * grow), r1 = __ldg(a.rgb + 3 * grow + 1), r2 = __ldg(a.rgb + 3 * grow + 2);
+        gz0 = __ldg(a.g_rgb + 3 * grow) * r0 * (1.f - r0);
+        gz1 = __ldg(a.g_rgb + 3 * grow + 1) * r1 * (1.f - r1);
+        gz2 = __ldg(a.g_rgb + 3 * grow + 2) * r2 * (1.f - r2);
+        const uint32_t smask = __ldg(mask_tile + kMaskSigmaWord * kTileM + row);
+        gsp = (smask & 1u) ? __ldg(a.g_sigma + grow) : 0.f;
+      }
+      if (half == 0) {
+        gz_out[3 * (tile * kTileM + row)] = gz0;
+        gz_out[3 * (tile * kTileM + row) + 1] = gz1;
+        gz_out[3 * (tile * kTileM + row) + 2] = gz2;
+        gsp_out[tile * kTileM + row] = gsp;
+      }
+      // ---- G9 = (gz . W_out) masked by h9 > 0; this half owns columns [64*half, 64*half + 64) = block `half`
+      {
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+#pragma unroll
+        for (int gi = 0; gi < 2; ++gi) {
+          const int col0 = half * 64 + gi * 32;
+          const uint32_t mk = __ldg(mask_tile + (64 + 2 * half + gi) * kTileM + row);
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float t = gz0 * sWout[col0 + i];
+            t = fmaf(gz1, sWout[128 + col0 + i], t);
+            t = fmaf(gz2, sWout[256 + col0 + i], t);
+            f[i] = ((mk >> i) & 1u) ? t : 0.f;
+          }
+          store_group_bf16(f, a_row + half * kBlockBytes, row, gi * 4);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          bulk_s2g(g_tile + (size_t)(kGradG9 + half) * kBlockBytes + q * 4096, sA + half * kBlockBytes + q * 4096, 4096);
+          bulk_commit();
+        }
+        mbar_arrive(&a_ready[half]);
+      }
+      for (int j = 0; j < kNumBwdLayers; ++j) {
+        if (j & 1) {
+          mbar_wait(&acc_full[1], accn1 & 1);
+          ++accn1;
+        } else {
+          mbar_wait(&acc_full[0], accn0 & 1);
+          ++accn0;
+        }
+        tc_fence_after();
+        const uint32_t taddr = lane_addr + (uint32_t)(j & 1) * 256u;
+        const int slot = 8 - j;  // ReLU mask of the layer output this gradient flows into (j >= 1): h7 .. h0
+#pragma unroll 1
+        for (int t = 0; t < 2; ++t) {
+          const int kb = half + 2 * t;
+          uint32_t v0[32], v1[32];
+          tmem_ld32(taddr + kb * 64, v0);
+          tmem_ld32(taddr + kb * 64 + 32, v1);
+          uint32_t m0 = 0xffffffffu, m1 = 0xffffffffu;
+          if (j >= 1) {
+            m0 = __ldg(mask_tile + (slot * 8 + 2 * kb) * kTileM + row);
+            m1 = __ldg(mask_tile + (slot * 8 + 2 * kb + 1) * kTileM + row);
+          }
+          if (lane == 0) {
+            // the bulk store that last read this warp's slice of block kb must be done: it is the newest group only
+            // for (j == 0, t == 0), where it is the G9 store of this tile
+            if (j == 0 && t == 0) bulk_wait_read<0>();
+            else bulk_wait_read<1>();
+          }
+          __syncwarp();
+          tmem_ld_wait();
+          uint8_t* blk_row = a_row + kb * kBlockBytes;
+          float f[32];
+          masked_group(v0, m0, gsp, j == 1 ? sW8 + kb * 64 : nullptr, f);
+          store_group_bf16(f, blk_row, row, 0);
+          masked_group(v1, m1, gsp, j == 1 ? sW8 + kb * 64 + 32 : nullptr, f);
+          store_group_bf16(f, blk_row, row, 4);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            bulk_s2g(g_tile + (size_t)(2 + 4 * j + kb) * kBlockBytes + q * 4096, sA + kb * kBlockBytes + q * 4096, 4096);
+            bulk_commit();
+          }
+          tc_fence_before();
+          if (j < kNumBwdLayers - 1) mbar_arrive(&a_ready[kb]);
+        }
+      }
+    }
+    if (lane == 0) bulk_wait_all<0>();
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ================================================================================================
+// 2. wgrad
+// ================================================================================================
+struct WUnit {
+  int g_blk0;      // first G block of the unit in the gradient tile image
+  int n_gblk;      // 2 or 4 (64 output features each)
+  int x_blk0;      // first X block in the cache tile image (contiguous blocks)
+  int n_xblk;      // full 64-column X blocks
+  int x_extra;     // extra narrow block (view-direction encoding, 32 columns) or -1
+  int param_w;     // weight gradient slot
+  int w_row0;      // first output row in the weight tensor
+  int w_col0;      // first input column
+  int w_ld;        // weight leading dimension
+  int valid_cols;  // accumulator columns that map to real weight columns
+  int param_b;     // bias slot or -1
+  int b_off;
+};
+constexpr int kNumWUnits = 11;
+__constant__ WUnit c_wunits[kNumWUnits];
+
+constexpr int kWgStages = 5;
+constexpr int kWgSlice = 4096;           // 32 rows of one block
+constexpr int kWgStageBytes = 9 * kWgSlice;
+constexpr int kWgThreads = 192;
+constexpr int kWgSmBar = kWgStages * kWgStageBytes;
+constexpr int kWgSmemBytes = kWgSmBar + 256 + 1024;
+
+struct WgradArgs {
+  const uint8_t* cache;
+  const uint8_t* scratch;
+  ParamPtrs grads;
+  int64_t m;
+};
+
+struct Segment {
+  int unit;
+  int64_t tile0, tile1;
+};
+
+// cost-balanced contiguous partition of (unit, tile) pairs over the grid
+__device__ __forceinline__ int unit_cost(int u) { return c_wunits[u].n_gblk + c_wunits[u].n_xblk + (c_wunits[u].x_extra >= 0 ? 1 : 0); }
+
+__device__ inline int build_segments(int64_t ntiles, Segment* seg) {
+  int64_t total = 0;
+  for (int u = 0; u < kNumWUnits; ++u) total += ntiles * unit_cost(u);
+  const int64_t lo = total * blockIdx.x / gridDim.x, hi = total * (blockIdx.x + 1) / gridDim.x;
+  int n = 0;
+  int64_t off = 0;
+  for (int u = 0; u < kNumWUnits; ++u) {
+    const int c = unit_cost(u);
+    const int64_t span = ntiles * c;
+    int64_t a = lo - off, b = hi - off;
+    if (a < 0) a = 0;
+    if (b > span) b = span;
+    if (b > a) {
+      const int64_t t0 = (a + c - 1) / c, t1 = (b + c - 1) / c;
+      if (t1 > t0) {
+        seg[n].unit = u;
+        seg[n].tile0 = t0;
+        seg[n].tile1 = t1 < ntiles ? t1 : ntiles;
+        ++n;
+      }
+    }
+    off += span;
+  }
+  return n;
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgSmBar);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kWgStages;
+  uint64_t* acc_done = bars + 2 * kWgStages;
+  uint64_t* acc_free = acc_done + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 1);
+  __shared__ Segment segs[kNumWUnits];
+  __shared__ int nseg_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ntiles = num_tiles(a.m);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWgStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1 + 4);  // MMA commit + the four column-sum warps
+    }
+    mbar_init(acc_done, 1);
+    mbar_init(acc_free, 128);
+    fence_barrier_init();
+    nseg_s = build_segments(ntiles, segs);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nseg = nseg_s;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ loader: 32-row slices of every block
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int si = 0; si < nseg; ++si) {
+        const WUnit u = c_wunits[segs[si].unit];
+        const int nblk = u.n_gblk + u.n_xblk + (u.x_extra >= 0 ? 1 : 0);
+        for (int64_t tile = segs[si].tile0; tile < segs[si].tile1; ++tile) {
+          const uint8_t* gsrc = a.scratch + (size_t)tile * kGradTileBytes + (size_t)u.g_blk0 * kBlockBytes;
+          const uint8_t* xsrc = a.cache + (size_t)tile * kCacheTileBytes;
+          for (int sl = 0; sl < 4; ++sl) {
+            const uint32_t s = g % kWgStages, ph = (g / kWgStages) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_arrive_expect_tx(&full[s], (uint32_t)nblk * kWgSlice);
+            uint8_t* dst = smem + s * kWgStageBytes;
+            for (int b = 0; b < u.n_gblk; ++b)
+              bulk_g2s(dst + b * kWgSlice, gsrc + (size_t)b * kBlockBytes + sl * kWgSlice, kWgSlice, &full[s]);
+            dst += u.n_gblk * kWgSlice;
+            for (int b = 0; b < u.n_xblk; ++b)
+              bulk_g2s(dst + b * kWgSlice, xsrc + (size_t)(u.x_blk0 + b) * kBlockBytes + sl * kWgSlice, kWgSlice, &full[s]);
+            if (u.x_extra >= 0)
+              bulk_g2s(dst + u.n_xblk * kWgSlice, xsrc + (size_t)u.x_extra * kBlockBytes + sl * kWgSlice, kWgSlice, &full[s]);
+            ++g;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (MN-major operands)
+    if (lane == 0) {
+      uint32_t g = 0;
+      const uint32_t sm_u = smem_u32(smem);
+      for (int si = 0; si < nseg; ++si) {
+        const WUnit u = c_wunits[segs[si].unit];
+        const int nhalf = u.n_gblk / 2;
+        const uint32_t n_main = (uint32_t)u.n_xblk * 64u;
+        const uint32_t idesc_main = make_idesc_bf16(n_main, true, true);
+        const uint32_t idesc_extra = make_idesc_bf16(32, true, true);
+        if (si > 0) mbar_wait(acc_free, (uint32_t)(si - 1) & 1);
+        tc_fence_after();
+        bool first = true;
+        for (int64_t tile = segs[si].tile0; tile < segs[si].tile1; ++tile) {
+          for (int sl = 0; sl < 4; ++sl) {
+            const uint32_t s = g % kWgStages, ph = (g / kWgStages) & 1;
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint32_t st = sm_u + s * kWgStageBytes;
+            const uint32_t xb = st + u.n_gblk * kWgSlice;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              for (int h = 0; h < nhalf; ++h) {
+                const uint64_t da = desc_mnmajor(st + (2 * h) * kWgSlice + k * 2048, kWgSlice);
+                const uint64_t db = desc_mnmajor(xb + k * 2048, kWgSlice);
+                umma_bf16(tmem_base + h * 256, da, db, idesc_main, first ? 0u : 1u);
+                if (u.x_extra >= 0) {
+                  const uint64_t de = desc_mnmajor(xb + u.n_xblk * kWgSlice + k * 2048, kWgSlice);
+                  umma_bf16(tmem_base + h * 256 + n_main, da, de, idesc_extra, first ? 0u : 1u);
+                }
+              }
+              first = false;
+            }
+            umma_commit(&empty[s]);
+            ++g;
+          }
+        }
+        umma_commit(acc_done);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ bias column sums + accumulator flush
+    const int q = warp & 3;
+    const int tid = (warp - 2) * 32 + lane;  // 0..127
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t g = 0;
+    for (int si = 0; si < nseg; ++si) {
+      const WUnit u = c_wunits[segs[si].unit];
+      const int ncol_pairs = u.n_gblk * 32;
+      const bool do_bias = u.param_b >= 0 && tid < ncol_pairs;
+      const int col = 2 * tid;
+      const uint32_t boff = (uint32_t)(col >> 6) * kWgSlice + ((col & 63) & 7) * 2;
+      const uint32_t chunk = (uint32_t)((col & 63) >> 3);
+      float b0 = 0.f, b1 = 0.f;
+      for (int64_t tile = segs[si].tile0; tile < segs[si].tile1; ++tile) {
+        for (int sl = 0; sl < 4; ++sl) {
+          const uint32_t s = g % kWgStages, ph = (g / kWgStages) & 1;
+          mbar_wait(&full[s], ph);
+          if (do_bias) {
+            const uint8_t* st = smem + s * kWgStageBytes + boff;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              const uint32_t w = *reinterpret_cast<const uint32_t*>(st + r * 128 + (((chunk ^ (uint32_t)(r & 7)) & 7u) << 4));
+              b0 += __uint_as_float(w << 16);
+              b1 += __uint_as_float(w & 0xffff0000u);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[s]);
+          ++g;
+        }
+      }
+      if (do_bias) {
+        float* db = a.grads.p[u.param_b] + u.b_off;
+        atomicAdd(db + col, b0);
+        atomicAdd(db + col + 1, b1);
+      }
+      // flush the accumulator of this segment
+      mbar_wait(acc_done, (uint32_t)si & 1);
+      tc_fence_after();
+      const int nhalf = u.n_gblk / 2;
+      const int ncols = u.n_xblk * 64 + (u.x_extra >= 0 ? 32 : 0);
+      float* dw = a.grads.p[u.param_w];
+      for (int h = 0; h < nhalf; ++h) {
+        const int out_row = u.w_row0 + h * 128 + q * 32 + lane;
+        float* dst = dw + (size_t)out_row * u.w_ld + u.w_col0;
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(lane_addr + h * 256 + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < u.valid_cols) atomicAdd(dst + c0 + i, __uint_as_float(v[i]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(acc_free);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static void build_wunits(WUnit* u) {
+  int n = 0;
+  auto add = [&](int g0, int ng, int x0, int nx, int xe, int pw, int row0, int col0, int ld, int valid, int pb, int boff) {
+    u[n++] = WUnit{g0, ng, x0, nx, xe, pw, row0, col0, ld, valid, pb, boff};
+  };
+  add(grad_g(0), 4, kCachePe, 1, -1, W_IN, 0, 0, kP, kP, B_IN, 0);                        // fc_in : G0 x pe
+  for (int l = 1; l <= 4; ++l) add(grad_g(l), 4, cache_h(l - 1), 4, -1, 2 * l, 0, 0, kF, kF, 2 * l + 1, 0);  // fc_1..4
+  add(grad_g(5), 4, kCachePe, 1, -1, W_5, 0, 0, kP + kF, kP, B_5, 0);                     // fc_5, position columns
+  add(grad_g(5), 4, cache_h(4), 4, -1, W_5, 0, kP, kP + kF, kF, -1, 0);                   // fc_5, h4 columns
+  add(grad_g(6), 4, cache_h(5), 4, -1, W_6, 0, 0, kF, kF, B_6, 0);
+  add(grad_g(7), 4, cache_h(6), 4, -1, W_7, 0, 0, kF, kF, B_7, 0);
+  add(kGradG8, 4, cache_h(7), 4, -1, W_8, 1, 0, kF, kF, B_8, 1);                          // fc_8 rows 1..256
+  add(kGradG9, 2, kCacheFeat, 4, kCacheDe, W_9, 0, 0, kF + kV, kF + kV, B_9, 0);          // fc_9 : G9 x [feat | de]
+}
+
+// ================================================================================================
+// 3. heads: d fc_out.{weight,bias} = gz^T h9, sum gz ;  d fc_8.{weight,bias}[0] = g_sigma_pre^T h7, sum g_sigma_pre
+// ================================================================================================
+struct HeadArgs {
+  const uint8_t* cache;
+  const uint8_t* scratch;
+  ParamPtrs grads;
+  int64_t m;
+};
+
+__device__ __forceinline__ float bf16_at(const uint8_t* block, int r, int k) {
+  const uint16_t v = *reinterpret_cast<const uint16_t*>(block + tile_off((uint32_t)r, (uint32_t)k));
+  return __uint_as_float((uint32_t)v << 16);
+}
+
+__global__ void __launch_bounds__(384) mlp_head_wgrad_kernel(HeadArgs a) {
+  __shared__ float sg[kTileM][4];
+  const int64_t ntiles = num_tiles(a.m);
+  const float* gz = reinterpret_cast<const float*>(a.scratch + scratch_gz_offset(a.m));
+  const float* gsp = reinterpret_cast<const float*>(a.scratch + scratch_gsp_offset(a.m));
+  const int tid = threadIdx.x;
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;  // threads 0..127: fc_out column tid; 128..383: fc_8 row-0 column tid-128
+  float bsum = 0.f;                           // thread c < 4: running sum of sg[:, c]
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    __syncthreads();
+    if (tid < kTileM) {
+      const int64_t r = tile * kTileM + tid;
+      sg[tid][0] = gz[3 * r], sg[tid][1] = gz[3 * r + 1], sg[tid][2] = gz[3 * r + 2], sg[tid][3] = gsp[r];
+    }
+    __syncthreads();
+    const uint8_t* ct = a.cache + (size_t)tile * kCacheTileBytes;
+    if (tid < kH) {
+      const uint8_t* blk = ct + (size_t)(kCacheH9 + (tid >> 6)) * kBlockBytes;
+#pragma unroll 4
+      for (int r = 0; r < kTileM; ++r) {
+        const float h = bf16_at(blk, r, tid & 63);
+        acc0 = fmaf(sg[r][0], h, acc0);
+        acc1 = fmaf(sg[r][1], h, acc1);
+        acc2 = fmaf(sg[r][2], h, acc2);
+      }
+    } else {
+      const int c = tid - kH;
+      const uint8_t* blk = ct + (size_t)(cache_h(7) + (c >> 6)) * kBlockBytes;
+#pragma unroll 4
+      for (int r = 0; r < kTileM; ++r) acc0 = fmaf(sg[r][3], bf16_at(blk, r, c & 63), acc0);
+    }
+    if (tid < 4)
+      for (int r = 0; r < kTileM; ++r) bsum += sg[r][tid];
+  }
+  if (tid < kH) {
+    atomicAdd(a.grads.p[W_OUT] + tid, acc0);
+    atomicAdd(a.grads.p[W_OUT] + kH + tid, acc1);
+    atomicAdd(a.grads.p[W_OUT] + 2 * kH + tid, acc2);
+  } else {
+    atomicAdd(a.grads.p[W_8] + (tid - kH), acc0);
+  }
+  if (tid < 3) atomicAdd(a.grads.p[B_OUT] + tid, bsum);
+  if (tid == 3) atomicAdd(a.grads.p[B_8], bsum);
+}
+
+__global__ void zero_grads_kernel(ParamPtrs g) {
+  const int sizes[22] = {kF * kP, kF, kF * kF, kF, kF * kF, kF, kF * kF, kF, kF * kF, kF, kF * (kP + kF), kF,
+                         kF * kF, kF, kF * kF, kF, (kF + 1) * kF, kF + 1, kH * (kF + kV), kH, 3 * kH, 3};
+  float* p = g.p[blockIdx.y];
+  const int n = sizes[blockIdx.y];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0.f;
+}
+
+static bool g_wunits_ready = false;
+
+}  // namespace nerf
+
+using namespace nerf;
+
+extern "C" int nerf_mlp_bf16_backward(const void* packed_dev, const void* cache_dev, const float* rgb_dev, int64_t m,
+                                      const float* g_sigma_dev, const float* g_rgb_dev, float* const* grads,
+                                      void* scratch_dev, nerf_stream_t stream) {
+  NERF_CHECK_ARG(m > 0, "nerf_mlp_bf16_backward: row count must be positive");
+  NERF_CHECK_ARG(packed_dev && cache_dev && rgb_dev && g_sigma_dev && g_rgb_dev && grads && scratch_dev,
+                 "nerf_mlp_bf16_backward: null pointer");
+  cudaStream_t st = as_stream(stream);
+  static bool attr_set = false;
+  if (!attr_set) {
+    NERF_CUDA(cudaFuncSetAttribute(mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDgSmemBytes));
+    NERF_CUDA(cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
+    attr_set = true;
+  }
+  if (!g_wunits_ready) {
+    WUnit table[kNumWUnits];
+    build_wunits(table);
+    NERF_CUDA(cudaMemcpyToSymbol(c_wunits, table, sizeof(table)));
+    g_wunits_ready = true;
+  }
+  ParamPtrs gp;
+  for (int i = 0; i < NERF_NUM_PARAM_TENSORS; ++i) {
+    NERF_CHECK_ARG(grads[i] != nullptr, "nerf_mlp_bf16_backward: null gradient pointer");
+    gp.p[i] = grads[i];
+  }
+  zero_grads_kernel<<<dim3(32, 22), 256, 0, st>>>(gp);
+  NERF_LAUNCH_CHECK();
+  const int64_t ntiles = num_tiles(m);
+  const int sms = sm_count();
+  {
+    DgradArgs a;
+    a.packed = reinterpret_cast<const uint8_t*>(packed_dev);
+    a.cache = reinterpret_cast<const uint8_t*>(cache_dev);
+    a.rgb = rgb_dev, a.g_sigma = g_sigma_dev, a.g_rgb = g_rgb_dev;
+    a.scratch = reinterpret_cast<uint8_t*>(scratch_dev);
+    a.m = m;
+    const int grid = (int)(ntiles < sms ? ntiles : sms);
+    mlp_dgrad_kernel<<<grid, kDgThreads, kDgSmemBytes, st>>>(a);
+    NERF_LAUNCH_CHECK();
+  }
+  {
+    WgradArgs a;
+    a.cache = reinterpret_cast<const uint8_t*>(cache_dev);
+    a.scratch = reinterpret_cast<const uint8_t*>(scratch_dev);
+    a.grads = gp;
+    a.m = m;
+    mlp_wgrad_kernel<<<sms, kWgThreads, kWgSmemBytes, st>>>(a);
+    NERF_LAUNCH_CHECK();
+  }
+  {
+    HeadArgs a;
+    a.cache = reinterpret_cast<const uint8_t*>(cache_dev);
+    a.scratch = reinterpret_cast<const uint8_t*>(scratch_dev);
+    a.grads = gp;
+    a.m = m;
+    const int grid = (int)(ntiles < 2 * sms ? ntiles : 2 * sms);
+    mlp_head_wgrad_kernel<<<grid, 384, 0, st>>>(a);
+    NERF_LAUNCH_CHECK();
+  }
+  return NERF_OK;
+}

@@ -1,0 +1,130 @@
+// Weight packing for the tensor-core chains: fp32 (out,in) nn.Linear weights (network/nerf.py:49-59) -> bf16
+// 128B-swizzled K-major chunks (N rows x 64 K-columns) in exactly the order the forward and dgrad chains stream
+// them, plus the fp32 constants the epilogues need.  Re-run after every optimizer step (2.3 MB written).
+#include "common.cuh"
+#include "mlp_tc_layout.cuh"
+#include "tc_common.cuh"
+
+namespace nerf {
+using namespace tc;
+
+struct PackChunk {
+  int param;      // index into the 22-pointer parameter array
+  int src_row0;   // first source row
+  int src_col0;   // first source column
+  int ld;         // source leading dimension
+  int nrows;      // destination rows (N of the MMA)
+  int valid_k;    // K columns copied; the rest of the 64 are zero
+  int transpose;  // 0: dst(n,k) = W[row0+n][col0+k]   1: dst(n,k) = W[row0+k][col0+n]
+  uint32_t dst_off;
+};
+constexpr int kMaxPackChunks = 96;
+__constant__ PackChunk c_pack[kMaxPackChunks];
+
+__global__ void __launch_bounds__(256) pack_weights_kernel(ParamPtrs params, uint8_t* __restrict__ packed) {
+  const PackChunk pc = c_pack[blockIdx.y];
+  int u = blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte unit (8 bf16) per thread
+  if (u >= pc.nrows * 8) return;
+  int n = u >> 3, j = u & 7;
+  const float* w = params.p[pc.param];
+  uint32_t out[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float v[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      int k = 8 * j + 2 * e + h;
+      float x = 0.f;
+      if (k < pc.valid_k)
+        x = pc.transpose ? w[(size_t)(pc.src_row0 + k) * pc.ld + pc.src_col0 + n]
+                         : w[(size_t)(pc.src_row0 + n) * pc.ld + pc.src_col0 + k];
+      v[h] = x;
+    }
+    out[e] = pack_bf16(v[0], v[1]);
+  }
+  uint4* dst = reinterpret_cast<uint4*>(packed + pc.dst_off + n * 128 + ((j ^ (n & 7)) << 4));
+  *dst = make_uint4(out[0], out[1], out[2], out[3]);
+}
+
+__global__ void pack_consts_kernel(ParamPtrs params, float* __restrict__ c) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kCFloats) return;
+  float v = 0.f;
+  if (i < kCBias8) v = params.p[2 * (i >> 8) + 1][i & 255];   // biases of fc_in, fc_1..fc_7
+  else if (i < kCBias9) v = params.p[B_8][1 + (i - kCBias8)];  // fc_8.bias[1:]
+  else if (i < kCW8Row0) v = params.p[B_9][i - kCBias9];
+  else if (i < kCWout) v = params.p[W_8][i - kCW8Row0];        // fc_8.weight[0, :]
+  else if (i < kCB8_0) v = params.p[W_OUT][i - kCWout];        // fc_out.weight (3,128)
+  else if (i == kCB8_0) v = params.p[B_8][0];
+  else if (i < kCBout + 3) v = params.p[B_OUT][i - kCBout];
+  c[i] = v;
+}
+
+static int build_pack_table(PackChunk* t) {
+  int n = 0;
+  uint32_t off = (uint32_t)kPackedFwdOff;
+  auto add = [&](int param, int row0, int col0, int ld, int nrows, int valid, int transpose) {
+    t[n++] = PackChunk{param, row0, col0, ld, nrows, valid, transpose, off};
+    off += (uint32_t)nrows * 128u;
+  };
+  // ---- forward chain (consumption order)
+  add(W_IN, 0, 0, kP, kF, kP, 0);
+  for (int l = 1; l <= 4; ++l)
+    for (int kb = 0; kb < 4; ++kb) add(2 * l, 0, 64 * kb, kF, kF, 64, 0);       // fc_1..fc_4
+  add(W_5, 0, 0, kP + kF, kF, kP, 0);                                           // fc_5, position columns
+  for (int kb = 0; kb < 4; ++kb) add(W_5, 0, kP + 64 * kb, kP + kF, kF, 64, 0);
+  for (int l = 6; l <= 7; ++l)
+    for (int kb = 0; kb < 4; ++kb) add(2 * l, 0, 64 * kb, kF, kF, 64, 0);       // fc_6, fc_7
+  for (int kb = 0; kb < 4; ++kb) add(W_8, 1, 64 * kb, kF, kF, 64, 0);           // fc_8 rows 1..256
+  for (int kb = 0; kb < 4; ++kb) add(W_9, 0, 64 * kb, kF + kV, kH, 64, 0);      // fc_9, feature columns
+  add(W_9, 0, kF, kF + kV, kH, kV, 0);                                          // fc_9, view columns
+  // ---- dgrad chain: dst(n = input feature, k = output feature)
+  off = (uint32_t)kPackedBwdOff;
+  for (int kb = 0; kb < 2; ++kb) add(W_9, 64 * kb, 0, kF + kV, kF, 64, 1);      // fc_9^T, feature inputs only
+  for (int kb = 0; kb < 4; ++kb) add(W_8, 1 + 64 * kb, 0, kF, kF, 64, 1);       // fc_8^T, feature rows
+  for (int kb = 0; kb < 4; ++kb) add(W_7, 64 * kb, 0, kF, kF, 64, 1);
+  for (int kb = 0; kb < 4; ++kb) add(W_6, 64 * kb, 0, kF, kF, 64, 1);
+  for (int kb = 0; kb < 4; ++kb) add(W_5, 64 * kb, kP, kP + kF, kF, 64, 1);     // fc_5^T, h4 columns only
+  for (int l = 4; l >= 1; --l)
+    for (int kb = 0; kb < 4; ++kb) add(2 * l, 64 * kb, 0, kF, kF, 64, 1);       // fc_4^T .. fc_1^T
+  return n;
+}
+
+static bool g_pack_table_ready = false;
+static int g_pack_chunks = 0;
+
+}  // namespace nerf
+
+using namespace nerf;
+
+extern "C" {
+
+size_t nerf_mlp_bf16_packed_bytes(void) { return kPackedBytes; }
+
+int nerf_mlp_bf16_pack(const float* const* params, void* packed_dev, nerf_stream_t stream) {
+  NERF_CHECK_ARG(params && packed_dev, "nerf_mlp_bf16_pack: null pointer");
+  cudaStream_t st = as_stream(stream);
+  if (!g_pack_table_ready) {
+    PackChunk table[kMaxPackChunks];
+    g_pack_chunks = build_pack_table(table);
+    NERF_CUDA(cudaMemcpyToSymbol(c_pack, table, sizeof(PackChunk) * g_pack_chunks));
+    g_pack_table_ready = true;
+  }
+  ParamPtrs pp;
+  for (int i = 0; i < NERF_NUM_PARAM_TENSORS; ++i) {
+    NERF_CHECK_ARG(params[i] != nullptr, "nerf_mlp_bf16_pack: null parameter pointer");
+    pp.p[i] = const_cast<float*>(params[i]);
+  }
+  dim3 grid((kF * 8 + 255) / 256, g_pack_chunks);
+  pack_weights_kernel<<<grid, 256, 0, st>>>(pp, reinterpret_cast<uint8_t*>(packed_dev));
+  NERF_LAUNCH_CHECK();
+  pack_consts_kernel<<<(kCFloats + 255) / 256, 256, 0, st>>>(
+      pp, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(packed_dev) + kPackedConstOff));
+  NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
+
+size_t nerf_mlp_bf16_cache_bytes(int64_t m) { return m > 0 ? cache_bytes(m) : 0; }
+size_t nerf_mlp_bf16_bwd_scratch_bytes(int64_t m) { return m > 0 ? scratch_bytes(m) : 0; }
+
+}  // extern "C"

@@ -1,0 +1,110 @@
+// Self test of the tensor-core building blocks: one tcgen05 tile with K-major and with MN-major operands, checked
+// against a plain matmul by tests/test_gpu_tensorcore.py (validates descriptors, swizzle and the TMEM layout).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace nerf {
+using namespace tc;
+
+// ------------------------------------------------------------------------------------------------
+// self test: one UMMA tile, both operand majors
+// ------------------------------------------------------------------------------------------------
+// variant 0: a (128 x k) row-major, b (n x k) row-major        -> K-major images
+// variant 1: a (k x 128) row-major (= A^T), b (k x n) row-major -> MN-major images (the wgrad form)
+__global__ void __launch_bounds__(128, 1) selftest_umma_kernel(const uint16_t* __restrict__ a,
+                                                               const uint16_t* __restrict__ b, float* __restrict__ d,
+                                                               int n, int k, int variant) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = k / 64;
+  uint8_t* sA;
+  uint8_t* sB;
+  uint32_t a_blk, b_blk;  // byte stride between 64-column blocks
+  if (variant == 0) {
+    a_blk = 128 * 128;
+    b_blk = n * 128;
+    sA = smem;
+    sB = smem + nkb * a_blk;
+    for (int e = threadIdx.x; e < 128 * k; e += 128) {
+      int r = e / k, c = e % k;
+      *reinterpret_cast<uint16_t*>(sA + (c / 64) * a_blk + tile_off(r, c % 64)) = a[e];
+    }
+    for (int e = threadIdx.x; e < n * k; e += 128) {
+      int r = e / k, c = e % k;
+      *reinterpret_cast<uint16_t*>(sB + (c / 64) * b_blk + tile_off(r, c % 64)) = b[e];
+    }
+  } else {
+    a_blk = k * 128;  // block = k rows x 64 M-columns
+    b_blk = k * 128;
+    sA = smem;
+    sB = smem + 2 * a_blk;
+    for (int e = threadIdx.x; e < k * 128; e += 128) {
+      int r = e / 128, c = e % 128;  // r = K index, c = M index
+      *reinterpret_cast<uint16_t*>(sA + (c / 64) * a_blk + tile_off(r, c % 64)) = a[e];
+    }
+    for (int e = threadIdx.x; e < k * n; e += 128) {
+      int r = e / n, c = e % n;
+      *reinterpret_cast<uint16_t*>(sB + (c / 64) * b_blk + tile_off(r, c % 64)) = b[e];
+    }
+  }
+  fence_proxy_async();
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = make_idesc_bf16((uint32_t)n, variant == 1, variant == 1);
+    for (int kk = 0; kk < k / 16; ++kk) {
+      uint64_t da, db;
+      if (variant == 0) {
+        da = desc_kmajor(smem_u32(sA) + (kk / 4) * a_blk + (kk % 4) * 32);
+        db = desc_kmajor(smem_u32(sB) + (kk / 4) * b_blk + (kk % 4) * 32);
+      } else {
+        da = desc_mnmajor(smem_u32(sA) + kk * 2048, a_blk);
+        db = desc_mnmajor(smem_u32(sB) + kk * 2048, b_blk);
+      }
+      umma_bf16(tmem_base, da, db, idesc, kk > 0 ? 1u : 0u);
+    }
+    umma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  const int row = warp * 32 + lane;
+  for (int c = 0; c < n / 32; ++c) {
+    uint32_t v[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c * 32, v);
+    tmem_ld_wait();
+    for (int i = 0; i < 32; ++i) d[(size_t)row * n + c * 32 + i] = __uint_as_float(v[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+}  // namespace nerf
+
+using namespace nerf;
+
+extern "C" {
+
+int nerf_selftest_umma(const uint16_t* a_dev, const uint16_t* b_dev, float* d_dev, int n, int k, int variant,
+                       nerf_stream_t stream) {
+  NERF_CHECK_ARG(a_dev && b_dev && d_dev, "nerf_selftest_umma: null pointer");
+  NERF_CHECK_ARG(n >= 64 && n <= 256 && n % 64 == 0 && k >= 64 && k <= 256 && k % 64 == 0 && (variant == 0 || variant == 1),
+                 "nerf_selftest_umma: n, k must be multiples of 64 in [64,256]; variant 0|1");
+  size_t smem = (size_t)128 * k * 2 + (size_t)n * k * 2 + 1024;
+  NERF_CUDA(cudaFuncSetAttribute(selftest_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  selftest_umma_kernel<<<1, 128, smem, as_stream(stream)>>>(a_dev, b_dev, d_dev, n, k, variant);
+  NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
+
+}  // extern "C"

@@ -62,6 +62,52 @@ class _MlpF32(torch.autograd.Function):
         return (None, None, None, *grads)
 
 
+class _MlpBf16(torch.autograd.Function):
+    """Fused encoding + MLP on the tensor cores, training form: forward fills the activation cache (tile images +
+    ReLU masks), backward runs the dgrad chain, wgrad and the head kernel."""
+
+    @staticmethod
+    def forward(ctx, net, pts, dirs, *params):
+        lib = _lib.load()
+        m = pts.shape[0]
+        dev = pts.device
+        pts_c = pts.detach().to(torch.float32).contiguous()
+        dirs_c = dirs.detach().to(torch.float32).contiguous()
+        packed = net.packed_weights()
+        sigma = torch.empty((m,), device=dev, dtype=torch.float32)
+        rgb = torch.empty((m, 3), device=dev, dtype=torch.float32)
+        cache = torch.empty((lib.nerf_mlp_bf16_cache_bytes(m),), device=dev, dtype=torch.uint8)
+        with torch.cuda.device(dev):
+            _lib.check(
+                lib.nerf_mlp_bf16_forward(_lib.ptr(packed, torch.uint8), _lib.ptr(pts_c), _lib.ptr(dirs_c), None, None, None,
+                                          0, m, _lib.ptr(sigma), _lib.ptr(rgb), _lib.ptr(cache, torch.uint8), _lib.stream()),
+                "nerf_mlp_bf16_forward",
+            )
+        ctx.net = net
+        ctx.save_for_backward(cache, rgb, packed)
+        ctx.shapes = [p.shape for p in params]
+        return sigma, rgb
+
+    @staticmethod
+    def backward(ctx, g_sigma, g_rgb):
+        lib = _lib.load()
+        cache, rgb, packed = ctx.saved_tensors
+        m = rgb.shape[0]
+        dev = rgb.device
+        g_sigma = torch.zeros((m,), device=dev) if g_sigma is None else g_sigma.to(torch.float32).contiguous()
+        g_rgb = torch.zeros((m, 3), device=dev) if g_rgb is None else g_rgb.to(torch.float32).contiguous()
+        grads = [torch.empty(s, device=dev, dtype=torch.float32) for s in ctx.shapes]
+        scratch = torch.empty((lib.nerf_mlp_bf16_bwd_scratch_bytes(m),), device=dev, dtype=torch.uint8)
+        with torch.cuda.device(dev):
+            _lib.check(
+                lib.nerf_mlp_bf16_backward(_lib.ptr(packed, torch.uint8), _lib.ptr(cache, torch.uint8), _lib.ptr(rgb), m,
+                                           _lib.ptr(g_sigma), _lib.ptr(g_rgb), _lib.pointer_array(grads),
+                                           _lib.ptr(scratch, torch.uint8), _lib.stream()),
+                "nerf_mlp_bf16_backward",
+            )
+        return (None, None, None, *grads)
+
+
 class NeRF(nn.Module):
     def __init__(self, pos_dim: int, view_dir_dim: int, feat_dim: int = 256, precision: str = "fp32"):
         super().__init__()
@@ -139,10 +185,13 @@ class NeRF(nn.Module):
         return self._packed
 
     def query_raw(self, pts: torch.Tensor, dirs: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        """Inference through the tcgen05 chain on RAW (M,3) points / directions (encoding fused in-kernel)."""
+        """The tcgen05 chain on RAW (M,3) points / directions (encoding fused in-kernel).  With autograd enabled
+        the training form runs (activation cache + tensor-core backward)."""
         lib = _lib.load()
         if not self.supports_bf16():
             raise ValueError("the bf16 tensor-core chain is built for NeRF(63, 27, 256)")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return _MlpBf16.apply(self, pts, dirs, *self.ordered_parameters())
         m = pts.shape[0]
         dev = pts.device
         packed = self.packed_weights()

@@ -66,7 +66,7 @@ class PrimitiveCube(PrimitiveBase):
         """pos, view_dir (N,S,3) -> sigma (N,S), radiance (N,S,3)   (cube.py:39-76)."""
         num_ray, num_sample = super().query_points(pos, view_dir)
         m = num_ray * num_sample
-        if self.fused_bf16_available() and not torch.is_grad_enabled():
+        if self.fused_bf16_available():
             sigma, radiance = self._radiance_field.query_raw(
                 pos.reshape(m, 3).to(torch.float32).contiguous(), view_dir.reshape(m, 3).to(torch.float32).contiguous()
             )
