@@ -184,6 +184,16 @@ int nerf_mlp_bf16_backward(const void* packed_dev, const void* cache_dev, const 
 int nerf_selftest_umma(const uint16_t* a_dev, const uint16_t* b_dev, float* d_dev, int n, int k, int variant,
                        nerf_stream_t stream);
 
+/* debugging aid: when buf_dev != NULL, CTA 0 of the next nerf_mlp_bf16_forward launches records, for its first
+ * `tiles` tiles and every layer, 4 SM-clock stamps (MMA layer start, MMA layer issued, accumulator seen by the
+ * epilogue, epilogue done) into buf_dev[(tile*10 + layer)*4 + k].  Pass NULL to switch it off. */
+int nerf_debug_set_profile_buffer(unsigned long long* buf_dev, int tiles);
+
+/* micro-benchmark: `blocks` CTAs each issue `iters` x 4 tcgen05.mma (M=128, N=n, K=16); cycles_dev[block] = SM cycles.
+ * mode 0: both operands from shared memory; mode 1: A operand from TMEM. */
+int nerf_selftest_mma_rate(int blocks, int iters, int n, int mode, unsigned long long* cycles_dev,
+                           nerf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

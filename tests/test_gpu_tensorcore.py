@@ -96,31 +96,33 @@ def test_bf16_query_through_primitive_cube(tn):
 
 
 @pytest.mark.parametrize("m", [300, 128 * 40, 128 * 313 + 5])
-def test_bf16_backward_vs_fp32_oracle(tn, m):
-    """Tensor-core training form (cache + dgrad chain + wgrad + heads) against the oracle's fp32 gradients."""
+def test_bf16_backward_vs_bf16_emulating_oracle(tn, m):
+    """Tensor-core training form (cache + dgrad chain + wgrad with heads) against the oracle that applies the same
+    bf16 rounding points on the CPU (oracle/nerf_oracle_bf16.py): tight agreement, so a kernel bug cannot hide
+    behind quantisation noise.  The fp32 oracle is compared loosely for reference."""
+    from oracle import nerf_oracle_bf16 as ob
+
     rng = np.random.default_rng(m)
     net, params = _scene(tn, seed=43)
     pts = (rng.normal(size=(m, 3)) * 1.5).astype(np.float32)
     dirs = rng.normal(size=(m, 3)).astype(np.float32)
     g_s = rng.normal(size=(m,)).astype(np.float32)
     g_c = rng.normal(size=(m, 3)).astype(np.float32)
-    pe = orc.positional_encode(pts, 10)
-    de = orc.positional_encode(dirs, 4)
-    s_o, c_o, acts = orc.nerf_forward(params, pe, de, return_cache=True)
-    grads_o = orc.nerf_backward(params, acts, g_s, g_c)
+    s_e, c_e, cache = ob.forward(params, pts, dirs)
+    grads_e = ob.backward(params, cache, g_s, g_c)
     sigma, rgb = net.query_raw(torch.from_numpy(pts).cuda(), torch.from_numpy(dirs).cuda())
     assert sigma.requires_grad
-    np.testing.assert_allclose(rgb.detach().cpu().numpy(), c_o, rtol=0, atol=2e-2)
-    np.testing.assert_allclose(sigma.detach().cpu().numpy(), s_o, rtol=0, atol=2e-2)
+    np.testing.assert_allclose(rgb.detach().cpu().numpy(), c_e, rtol=0, atol=2e-3)
+    np.testing.assert_allclose(sigma.detach().cpu().numpy(), s_e, rtol=0, atol=2e-3)
     ((sigma * torch.from_numpy(g_s).cuda()).sum() + (rgb * torch.from_numpy(g_c).cuda()).sum()).backward()
     torch.cuda.synchronize()
+    report = []
     for k, prm in net.named_parameters():
-        ref = grads_o[k]
+        ref = grads_e[k]
         got = prm.grad.cpu().numpy()
         assert np.isfinite(got).all(), k
-        scale = np.abs(ref).max() + 1e-8
-        err = np.abs(got - ref).max() / scale
-        # bf16 operands (8 mantissa bits) through up to 9 chained layers, fp32 accumulation over m rows
-        assert err < 4e-2, (k, err)
+        err = np.abs(got - ref).max() / (np.abs(ref).max() + 1e-8)
         cos = float((got * ref).sum() / (np.linalg.norm(got) * np.linalg.norm(ref) + 1e-30))
-        assert cos > 0.999, (k, cos)
+        report.append((k, float(err), cos))
+    bad = [r for r in report if r[1] > 3e-2 or r[2] < 0.9995]
+    assert not bad, "\n".join(f"{k}: relmax {e:.4f} cos {c:.6f}" for k, e, c in report)

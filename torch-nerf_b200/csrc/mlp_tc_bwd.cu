@@ -1,4 +1,4 @@
-// K6 on the sm_100a tensor cores: backward of the NeRF MLP (autograd of network/nerf.py:102-119) in three kernels.
+// K6 on the sm_100a tensor cores: backward of the NeRF MLP (autograd of network/nerf.py:102-119) in two kernels.
 //
 //  1. mlp_dgrad_kernel  -- the activation-gradient chain, same structure as the forward chain: per 128-row tile
 //        G9 = (g_rgb * rgb(1-rgb)) . W_out  masked by h9>0          (CUDA cores, 3 -> 128)
@@ -6,12 +6,12 @@
 //        j = 1: G7 = (G8feat . W8[1:, :] + g_sigma_pre (x) W8[0, :]) masked by h7>0
 //        j = 2..8: G6 .. G0                                          (fc_5 uses only its h4 columns)
 //     every G is written to the backward scratch as a tile image for wgrad; ReLU masks come from the bit words
-//     the forward pass saved.  gz (M,3) and g_sigma_pre (M) are written as fp32 for the head kernel.
+//     the forward pass saved.  {gz, g_sigma_pre} are written per row as one fp32 float4 for the head gradients.
 //  2. mlp_wgrad_kernel  -- dW_l = G_l^T . X_l as split-K tcgen05 GEMMs over the saved tile images, both operands
 //     MN-major (rows = reduction index); a persistent CTA streams 32-row slices through a 5-stage bulk-copy ring,
 //     keeps a (2 x 128) x N fp32 accumulator in TMEM and flushes it with fp32 atomics at segment boundaries;
-//     bias gradients are column sums of the G slices taken from shared memory by otherwise idle warps.
-//  3. mlp_head_wgrad_kernel -- the two fp32 heads (fc_out, and row 0 of fc_8 = density) on CUDA cores.
+//     bias gradients are column sums of the G slices taken from shared memory by otherwise idle warps, which also
+//     accumulate the two fp32 heads (fc_out, and row 0 of fc_8 = density) from the X slices already in smem.
 //
 // HBM-bound by design: wgrad must read G and X (2 x 512 B per row and layer); the chain kernels are tensor-bound.
 #include <cuda_bf16.h>
@@ -164,8 +164,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t accn0 = 0, accn1 = 0;
     uint8_t* a_row = sA + row * 128;
-    float* gz_out = reinterpret_cast<float*>(a.scratch + scratch_gz_offset(a.m));
-    float* gsp_out = reinterpret_cast<float*>(a.scratch + scratch_gsp_offset(a.m));
+    float4* ghead_out = reinterpret_cast<float4*>(a.scratch + scratch_ghead_offset(a.m));
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t grow = tile * kTileM + row;
       uint8_t* g_tile = a.scratch + (size_t)tile * kGradTileBytes;
@@ -181,12 +180,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
         const uint32_t smask = __ldg(mask_tile + kMaskSigmaWord * kTileM + row);
         gsp = (smask & 1u) ? __ldg(a.g_sigma + grow) : 0.f;
       }
-      if (half == 0) {
-        gz_out[3 * (tile * kTileM + row)] = gz0;
-        gz_out[3 * (tile * kTileM + row) + 1] = gz1;
-        gz_out[3 * (tile * kTileM + row) + 2] = gz2;
-        gsp_out[tile * kTileM + row] = gsp;
-      }
+      if (half == 0) ghead_out[tile * kTileM + row] = make_float4(gz0, gz1, gz2, gsp);
       // ---- G9 = (gz . W_out) masked by h9 > 0; this half owns columns [64*half, 64*half + 64) = block `half`
       {
         if (lane == 0) bulk_wait_read<1>();
@@ -276,7 +270,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
 // ================================================================================================
 struct WUnit {
   int g_blk0;      // first G block of the unit in the gradient tile image
-  int n_gblk;      // 2 or 4 (64 output features each)
+  int n_gblk;      // 0 (head-only unit), 2 or 4 (64 output features each)
   int x_blk0;      // first X block in the cache tile image (contiguous blocks)
   int n_xblk;      // full 64-column X blocks
   int x_extra;     // extra narrow block (view-direction encoding, 32 columns) or -1
@@ -287,13 +281,16 @@ struct WUnit {
   int valid_cols;  // accumulator columns that map to real weight columns
   int param_b;     // bias slot or -1
   int b_off;
+  int head;        // 0: none; 1: density head (d fc_8.weight[0,:], d fc_8.bias[0]) from g_sigma_pre and the X slices
+                   // 2: fc_out (d fc_out.weight, d fc_out.bias) from gz and the X slices (X = h9, no MMA)
 };
-constexpr int kNumWUnits = 11;
+constexpr int kNumWUnits = 12;
 __constant__ WUnit c_wunits[kNumWUnits];
 
 constexpr int kWgStages = 5;
-constexpr int kWgSlice = 4096;           // 32 rows of one block
-constexpr int kWgStageBytes = 9 * kWgSlice;
+constexpr int kWgSlice = 4096;            // 32 rows of one block
+constexpr int kWgHeadOff = 9 * kWgSlice;  // 32 x float4 head gradients
+constexpr int kWgStageBytes = kWgHeadOff + 1024;
 constexpr int kWgThreads = 192;
 constexpr int kWgSmBar = kWgStages * kWgStageBytes;
 constexpr int kWgSmemBytes = kWgSmBar + 256 + 1024;
@@ -311,7 +308,9 @@ struct Segment {
 };
 
 // cost-balanced contiguous partition of (unit, tile) pairs over the grid
-__device__ __forceinline__ int unit_cost(int u) { return c_wunits[u].n_gblk + c_wunits[u].n_xblk + (c_wunits[u].x_extra >= 0 ? 1 : 0); }
+__device__ __forceinline__ int unit_cost(int u) {
+  return c_wunits[u].n_gblk + c_wunits[u].n_xblk + (c_wunits[u].x_extra >= 0 ? 1 : 0);
+}
 
 __device__ inline int build_segments(int64_t ntiles, Segment* seg) {
   int64_t total = 0;
@@ -339,6 +338,9 @@ __device__ inline int build_segments(int64_t ntiles, Segment* seg) {
   return n;
 }
 
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
 __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -356,7 +358,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < kWgStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1 + 4);  // MMA commit + the four column-sum warps
+      mbar_init(&empty[i], 1 + 4);  // MMA commit + the four CUDA-core warps
     }
     mbar_init(acc_done, 1);
     mbar_init(acc_free, 128);
@@ -374,24 +376,27 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
     // ------------------------------------------------------------------ loader: 32-row slices of every block
     if (lane == 0) {
       uint32_t g = 0;
+      const uint8_t* ghead = a.scratch + scratch_ghead_offset(a.m);
       for (int si = 0; si < nseg; ++si) {
         const WUnit u = c_wunits[segs[si].unit];
-        const int nblk = u.n_gblk + u.n_xblk + (u.x_extra >= 0 ? 1 : 0);
+        const int nxb = u.n_xblk + (u.x_extra >= 0 ? 1 : 0);
+        const uint32_t bytes = (uint32_t)(u.n_gblk + nxb) * kWgSlice + (u.head ? 512u : 0u);
         for (int64_t tile = segs[si].tile0; tile < segs[si].tile1; ++tile) {
           const uint8_t* gsrc = a.scratch + (size_t)tile * kGradTileBytes + (size_t)u.g_blk0 * kBlockBytes;
           const uint8_t* xsrc = a.cache + (size_t)tile * kCacheTileBytes;
           for (int sl = 0; sl < 4; ++sl) {
             const uint32_t s = g % kWgStages, ph = (g / kWgStages) & 1;
             mbar_wait(&empty[s], ph ^ 1);
-            mbar_arrive_expect_tx(&full[s], (uint32_t)nblk * kWgSlice);
+            mbar_arrive_expect_tx(&full[s], bytes);
             uint8_t* dst = smem + s * kWgStageBytes;
             for (int b = 0; b < u.n_gblk; ++b)
               bulk_g2s(dst + b * kWgSlice, gsrc + (size_t)b * kBlockBytes + sl * kWgSlice, kWgSlice, &full[s]);
-            dst += u.n_gblk * kWgSlice;
+            uint8_t* xdst = dst + u.n_gblk * kWgSlice;
             for (int b = 0; b < u.n_xblk; ++b)
-              bulk_g2s(dst + b * kWgSlice, xsrc + (size_t)(u.x_blk0 + b) * kBlockBytes + sl * kWgSlice, kWgSlice, &full[s]);
+              bulk_g2s(xdst + b * kWgSlice, xsrc + (size_t)(u.x_blk0 + b) * kBlockBytes + sl * kWgSlice, kWgSlice, &full[s]);
             if (u.x_extra >= 0)
-              bulk_g2s(dst + u.n_xblk * kWgSlice, xsrc + (size_t)u.x_extra * kBlockBytes + sl * kWgSlice, kWgSlice, &full[s]);
+              bulk_g2s(xdst + u.n_xblk * kWgSlice, xsrc + (size_t)u.x_extra * kBlockBytes + sl * kWgSlice, kWgSlice, &full[s]);
+            if (u.head) bulk_g2s(dst + kWgHeadOff, ghead + ((size_t)tile * kTileM + sl * 32) * 16, 512, &full[s]);
             ++g;
           }
         }
@@ -439,30 +444,58 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
       }
     }
   } else {
-    // ------------------------------------------------------------------ bias column sums + accumulator flush
+    // ------------------------------------------------------------------ bias / head sums on CUDA cores + accumulator flush
     const int q = warp & 3;
     const int tid = (warp - 2) * 32 + lane;  // 0..127
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t g = 0;
     for (int si = 0; si < nseg; ++si) {
       const WUnit u = c_wunits[segs[si].unit];
-      const int ncol_pairs = u.n_gblk * 32;
-      const bool do_bias = u.param_b >= 0 && tid < ncol_pairs;
-      const int col = 2 * tid;
-      const uint32_t boff = (uint32_t)(col >> 6) * kWgSlice + ((col & 63) & 7) * 2;
+      const bool do_bias = u.param_b >= 0 && tid < u.n_gblk * 32;
+      const bool do_head = u.head != 0 && tid < u.n_xblk * 32;
+      const int col = 2 * tid;  // this thread's column pair, in G (bias) and in X (heads)
+      const uint32_t coff = (uint32_t)(col >> 6) * kWgSlice + ((col & 63) & 7) * 2;
       const uint32_t chunk = (uint32_t)((col & 63) >> 3);
-      float b0 = 0.f, b1 = 0.f;
+      float b0 = 0.f, b1 = 0.f;                                                 // bias column sums
+      float h00 = 0.f, h01 = 0.f, h10 = 0.f, h11 = 0.f, h20 = 0.f, h21 = 0.f;  // head sums [j][column of the pair]
+      float hb = 0.f;                                                           // head bias sums (threads 0..3)
       for (int64_t tile = segs[si].tile0; tile < segs[si].tile1; ++tile) {
         for (int sl = 0; sl < 4; ++sl) {
           const uint32_t s = g % kWgStages, ph = (g / kWgStages) & 1;
           mbar_wait(&full[s], ph);
+          const uint8_t* st = smem + s * kWgStageBytes;
           if (do_bias) {
-            const uint8_t* st = smem + s * kWgStageBytes + boff;
+            const uint8_t* gs = st + coff;
 #pragma unroll 8
             for (int r = 0; r < 32; ++r) {
-              const uint32_t w = *reinterpret_cast<const uint32_t*>(st + r * 128 + (((chunk ^ (uint32_t)(r & 7)) & 7u) << 4));
-              b0 += __uint_as_float(w << 16);
-              b1 += __uint_as_float(w & 0xffff0000u);
+              const uint32_t w = *reinterpret_cast<const uint32_t*>(gs + r * 128 + (((chunk ^ (uint32_t)(r & 7)) & 7u) << 4));
+              b0 += bf16_lo(w);
+              b1 += bf16_hi(w);
+            }
+          }
+          if (u.head) {
+            const float4* gh = reinterpret_cast<const float4*>(st + kWgHeadOff);
+            if (do_head) {
+              const uint8_t* xs = st + u.n_gblk * kWgSlice + coff;
+#pragma unroll 8
+              for (int r = 0; r < 32; ++r) {
+                const uint32_t w = *reinterpret_cast<const uint32_t*>(xs + r * 128 + (((chunk ^ (uint32_t)(r & 7)) & 7u) << 4));
+                const float x0 = bf16_lo(w), x1 = bf16_hi(w);
+                const float4 gv = gh[r];
+                if (u.head == 1) {
+                  h00 = fmaf(gv.w, x0, h00);
+                  h01 = fmaf(gv.w, x1, h01);
+                } else {
+                  h00 = fmaf(gv.x, x0, h00), h01 = fmaf(gv.x, x1, h01);
+                  h10 = fmaf(gv.y, x0, h10), h11 = fmaf(gv.y, x1, h11);
+                  h20 = fmaf(gv.z, x0, h20), h21 = fmaf(gv.z, x1, h21);
+                }
+              }
+            }
+            if (tid < 4) {
+              const float* ghf = reinterpret_cast<const float*>(gh);
+#pragma unroll 8
+              for (int r = 0; r < 32; ++r) hb += ghf[4 * r + tid];
             }
           }
           __syncwarp();
@@ -474,6 +507,21 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
         float* db = a.grads.p[u.param_b] + u.b_off;
         atomicAdd(db + col, b0);
         atomicAdd(db + col + 1, b1);
+      }
+      if (u.head == 1) {
+        if (do_head) {
+          atomicAdd(a.grads.p[W_8] + col, h00);  // d fc_8.weight[0, col]
+          atomicAdd(a.grads.p[W_8] + col + 1, h01);
+        }
+        if (tid == 3) atomicAdd(a.grads.p[B_8], hb);  // d fc_8.bias[0] = sum g_sigma_pre
+      } else if (u.head == 2) {
+        if (do_head) {
+          float* dw = a.grads.p[W_OUT];
+          atomicAdd(dw + col, h00), atomicAdd(dw + col + 1, h01);
+          atomicAdd(dw + kH + col, h10), atomicAdd(dw + kH + col + 1, h11);
+          atomicAdd(dw + 2 * kH + col, h20), atomicAdd(dw + 2 * kH + col + 1, h21);
+        }
+        if (tid < 3) atomicAdd(a.grads.p[B_OUT] + tid, hb);
       }
       // flush the accumulator of this segment
       mbar_wait(acc_done, (uint32_t)si & 1);
@@ -507,77 +555,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
 
 static void build_wunits(WUnit* u) {
   int n = 0;
-  auto add = [&](int g0, int ng, int x0, int nx, int xe, int pw, int row0, int col0, int ld, int valid, int pb, int boff) {
-    u[n++] = WUnit{g0, ng, x0, nx, xe, pw, row0, col0, ld, valid, pb, boff};
-  };
-  add(grad_g(0), 4, kCachePe, 1, -1, W_IN, 0, 0, kP, kP, B_IN, 0);                        // fc_in : G0 x pe
-  for (int l = 1; l <= 4; ++l) add(grad_g(l), 4, cache_h(l - 1), 4, -1, 2 * l, 0, 0, kF, kF, 2 * l + 1, 0);  // fc_1..4
-  add(grad_g(5), 4, kCachePe, 1, -1, W_5, 0, 0, kP + kF, kP, B_5, 0);                     // fc_5, position columns
-  add(grad_g(5), 4, cache_h(4), 4, -1, W_5, 0, kP, kP + kF, kF, -1, 0);                   // fc_5, h4 columns
-  add(grad_g(6), 4, cache_h(5), 4, -1, W_6, 0, 0, kF, kF, B_6, 0);
-  add(grad_g(7), 4, cache_h(6), 4, -1, W_7, 0, 0, kF, kF, B_7, 0);
-  add(kGradG8, 4, cache_h(7), 4, -1, W_8, 1, 0, kF, kF, B_8, 1);                          // fc_8 rows 1..256
-  add(kGradG9, 2, kCacheFeat, 4, kCacheDe, W_9, 0, 0, kF + kV, kF + kV, B_9, 0);          // fc_9 : G9 x [feat | de]
-}
-
-// ================================================================================================
-// 3. heads: d fc_out.{weight,bias} = gz^T h9, sum gz ;  d fc_8.{weight,bias}[0] = g_sigma_pre^T h7, sum g_sigma_pre
-// ================================================================================================
-struct HeadArgs {
-  const uint8_t* cache;
-  const uint8_t* scratch;
-  ParamPtrs grads;
-  int64_t m;
-};
-
-__device__ __forceinline__ float bf16_at(const uint8_t* block, int r, int k) {
-  const uint16_t v = *reinterpret_cast<const uint16_t*>(block + tile_off((uint32_t)r, (uint32_t)k));
-  return __uint_as_float((uint32_t)v << 16);
-}
-
-__global__ void __launch_bounds__(384) mlp_head_wgrad_kernel(HeadArgs a) {
-  __shared__ float sg[kTileM][4];
-  const int64_t ntiles = num_tiles(a.m);
-  const float* gz = reinterpret_cast<const float*>(a.scratch + scratch_gz_offset(a.m));
-  const float* gsp = reinterpret_cast<const float*>(a.scratch + scratch_gsp_offset(a.m));
-  const int tid = threadIdx.x;
-  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;  // threads 0..127: fc_out column tid; 128..383: fc_8 row-0 column tid-128
-  float bsum = 0.f;                           // thread c < 4: running sum of sg[:, c]
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    __syncthreads();
-    if (tid < kTileM) {
-      const int64_t r = tile * kTileM + tid;
-      sg[tid][0] = gz[3 * r], sg[tid][1] = gz[3 * r + 1], sg[tid][2] = gz[3 * r + 2], sg[tid][3] = gsp[r];
-    }
-    __syncthreads();
-    const uint8_t* ct = a.cache + (size_t)tile * kCacheTileBytes;
-    if (tid < kH) {
-      const uint8_t* blk = ct + (size_t)(kCacheH9 + (tid >> 6)) * kBlockBytes;
-#pragma unroll 4
-      for (int r = 0; r < kTileM; ++r) {
-        const float h = bf16_at(blk, r, tid & 63);
-        acc0 = fmaf(sg[r][0], h, acc0);
-        acc1 = fmaf(sg[r][1], h, acc1);
-        acc2 = fmaf(sg[r][2], h, acc2);
-      }
-    } else {
-      const int c = tid - kH;
-      const uint8_t* blk = ct + (size_t)(cache_h(7) + (c >> 6)) * kBlockBytes;
-#pragma unroll 4
-      for (int r = 0; r < kTileM; ++r) acc0 = fmaf(sg[r][3], bf16_at(blk, r, c & 63), acc0);
-    }
-    if (tid < 4)
-      for (int r = 0; r < kTileM; ++r) bsum += sg[r][tid];
-  }
-  if (tid < kH) {
-    atomicAdd(a.grads.p[W_OUT] + tid, acc0);
-    atomicAdd(a.grads.p[W_OUT] + kH + tid, acc1);
-    atomicAdd(a.grads.p[W_OUT] + 2 * kH + tid, acc2);
-  } else {
-    atomicAdd(a.grads.p[W_8] + (tid - kH), acc0);
-  }
-  if (tid < 3) atomicAdd(a.grads.p[B_OUT] + tid, bsum);
-  if (tid == 3) atomicAdd(a.grads.p[B_8], bsum);
+  auto add = [&](int g0, int ng, int x0, int nx, int xe, int pw, int row0, int col0, int ld, int valid, int pb, int boff,
+                 int head) { u[n++] = WUnit{g0, ng, x0, nx, xe, pw, row0, col0, ld, valid, pb, boff, head}; };
+  add(grad_g(0), 4, kCachePe, 1, -1, W_IN, 0, 0, kP, kP, B_IN, 0, 0);                      // fc_in : G0 x pe
+  for (int l = 1; l <= 4; ++l) add(grad_g(l), 4, cache_h(l - 1), 4, -1, 2 * l, 0, 0, kF, kF, 2 * l + 1, 0, 0);  // fc_1..4
+  add(grad_g(5), 4, kCachePe, 1, -1, W_5, 0, 0, kP + kF, kP, B_5, 0, 0);                   // fc_5, position columns
+  add(grad_g(5), 4, cache_h(4), 4, -1, W_5, 0, kP, kP + kF, kF, -1, 0, 0);                 // fc_5, h4 columns
+  add(grad_g(6), 4, cache_h(5), 4, -1, W_6, 0, 0, kF, kF, B_6, 0, 0);
+  add(grad_g(7), 4, cache_h(6), 4, -1, W_7, 0, 0, kF, kF, B_7, 0, 0);
+  add(kGradG8, 4, cache_h(7), 4, -1, W_8, 1, 0, kF, kF, B_8, 1, 1);                        // fc_8 rows 1..256 + density row
+  add(kGradG9, 2, kCacheFeat, 4, kCacheDe, W_9, 0, 0, kF + kV, kF + kV, B_9, 0, 0);        // fc_9 : G9 x [feat | de]
+  add(0, 0, kCacheH9, 2, -1, W_OUT, 0, 0, kH, 0, -1, 0, 2);                                // fc_out (CUDA cores only)
 }
 
 __global__ void zero_grads_kernel(ParamPtrs g) {
@@ -640,16 +628,6 @@ extern "C" int nerf_mlp_bf16_backward(const void* packed_dev, const void* cache_
     a.grads = gp;
     a.m = m;
     mlp_wgrad_kernel<<<sms, kWgThreads, kWgSmemBytes, st>>>(a);
-    NERF_LAUNCH_CHECK();
-  }
-  {
-    HeadArgs a;
-    a.cache = reinterpret_cast<const uint8_t*>(cache_dev);
-    a.scratch = reinterpret_cast<const uint8_t*>(scratch_dev);
-    a.grads = gp;
-    a.m = m;
-    const int grid = (int)(ntiles < 2 * sms ? ntiles : 2 * sms);
-    mlp_head_wgrad_kernel<<<grid, 384, 0, st>>>(a);
     NERF_LAUNCH_CHECK();
   }
   return NERF_OK;

@@ -53,6 +53,8 @@ struct FwdArgs {
   float* sigma;
   float* rgb;
   uint8_t* cache;       // training cache or null
+  unsigned long long* prof;  // optional timeline of CTA 0 (nerf_debug_set_profile_buffer)
+  int prof_tiles;
 };
 
 // [v | sin(2^l v) | cos(2^l v)]_{l<L} for a 3-vector, written as bf16 into the first NCHUNK 16-byte chunks of a
@@ -192,6 +194,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
           const uint32_t acc = tmem_base + (uint32_t)(l & 1) * 256u;
           const uint32_t idesc = (l == 9) ? idesc128 : idesc256;
           const int nk = fwd_nk(l);
+          const bool stamp = a.prof != nullptr && blockIdx.x == 0 && (int)in_cnt <= a.prof_tiles;
+          if (stamp) a.prof[(((int)in_cnt - 1) * kNumFwdLayers + l) * 4 + 0] = clock64();
           for (int kb = 0; kb < nk; ++kb) {
             uint32_t a_addr;
             int nsteps = 4;
@@ -217,6 +221,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
             ++g;
           }
           umma_commit(&acc_full[l & 1]);
+          if (stamp) a.prof[(((int)in_cnt - 1) * kNumFwdLayers + l) * 4 + 1] = clock64();
         }
         a_cnt += 9;
       }
@@ -229,8 +234,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t accn0 = 0, accn1 = 0;
     uint8_t* a_row = sA + row * 128;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int tile_iter = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_iter) {
       const int64_t grow = tile * kTileM + row;
+      const bool stamp = a.prof != nullptr && blockIdx.x == 0 && tile_iter < a.prof_tiles && warp == 2 && lane == 0;
       uint8_t* cache_tile = kTrain ? a.cache + (size_t)tile * kCacheTileBytes : nullptr;
       uint32_t* mask_tile =
           kTrain ? reinterpret_cast<uint32_t*>(a.cache + cache_mask_offset(a.m) + (size_t)tile * kMaskTileBytes) : nullptr;
@@ -284,6 +291,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
           ++accn0;
         }
         tc_fence_after();
+        if (stamp) a.prof[((tile_iter * kNumFwdLayers + l) * 4) + 2] = clock64();
         const uint32_t taddr = lane_addr + (uint32_t)(l & 1) * 256u;
         const float* bias = sC + ((l < 8) ? kCBias + 256 * l : (l == 8 ? kCBias8 : kCBias9));
         if (l < 9) {
@@ -329,6 +337,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
             mbar_arrive(&a_ready[kb]);
           }
           if (l == 7 && half == 1) sX[row * 4 + 3] = sigma_part;
+          if (stamp) a.prof[((tile_iter * kNumFwdLayers + l) * 4) + 3] = clock64();
         } else {
           // fc_9 output (128 columns): this half owns columns [64*half, 64*half + 64)
           uint32_t v0[32], v1[32];
@@ -387,6 +396,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
             }
             if (kTrain) mask_tile[kMaskSigmaWord * kTileM + row] = (grow < a.m && sp > 0.f) ? 1u : 0u;
           }
+          if (stamp) a.prof[((tile_iter * kNumFwdLayers + l) * 4) + 3] = clock64();
         }
       }
     }
@@ -403,9 +413,18 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
   }
 }
 
+static unsigned long long* g_prof_buf = nullptr;
+static int g_prof_tiles = 0;
+
 }  // namespace nerf
 
 using namespace nerf;
+
+extern "C" int nerf_debug_set_profile_buffer(unsigned long long* buf_dev, int tiles) {
+  g_prof_buf = buf_dev;
+  g_prof_tiles = tiles;
+  return NERF_OK;
+}
 
 extern "C" int nerf_mlp_bf16_forward(const void* packed_dev, const float* pts_dev, const float* dirs_dev,
                                      const float* ray_o_dev, const float* ray_d_dev, const float* t_dev, int s,
@@ -427,6 +446,8 @@ extern "C" int nerf_mlp_bf16_forward(const void* packed_dev, const float* pts_de
   a.pts = pts_dev, a.dirs = dirs_dev, a.ray_o = ray_o_dev, a.ray_d = ray_d_dev, a.t = t_dev, a.s = s, a.m = m;
   a.sigma = sigma_dev, a.rgb = rgb_dev;
   a.cache = reinterpret_cast<uint8_t*>(cache_dev);
+  a.prof = g_prof_buf;
+  a.prof_tiles = g_prof_tiles;
   const int64_t ntiles = num_tiles(m);
   const int grid = (int)((ntiles < sm_count()) ? ntiles : sm_count());
   if (cache_dev)

@@ -6,7 +6,7 @@
 //
 //   packed weights : [forward chunks][dgrad (transposed) chunks][fp32 constants]
 //   training cache : per 128-row tile 40 activation blocks, then per tile 69 x 128 ReLU-mask words
-//   bwd scratch    : per tile 38 gradient blocks, then gz (M,3) fp32 and g_sigma_pre (M) fp32
+//   bwd scratch    : per tile 38 gradient blocks, then per row float4 {gz0, gz1, gz2, g_sigma_pre}
 #pragma once
 
 #include <stddef.h>
@@ -71,9 +71,9 @@ constexpr int kGradG8 = 2;                                   // feature part of 
 __host__ __device__ constexpr int grad_g(int l) { return 6 + 4 * (7 - l); }  // G_l for l = 7..0
 constexpr int kGradBlocks = 38;
 constexpr size_t kGradTileBytes = (size_t)kGradBlocks * kBlockBytes;
-__host__ __device__ inline size_t scratch_gz_offset(int64_t m) { return (size_t)num_tiles(m) * kGradTileBytes; }
-__host__ __device__ inline size_t scratch_gsp_offset(int64_t m) { return scratch_gz_offset(m) + (size_t)num_tiles(m) * kTileM * 12; }
-__host__ __device__ inline size_t scratch_bytes(int64_t m) { return scratch_gsp_offset(m) + (size_t)num_tiles(m) * kTileM * 4; }
+// head gradients per row as float4 {gz0, gz1, gz2, g_sigma_pre} (gz = dL/d(fc_out pre-sigmoid))
+__host__ __device__ inline size_t scratch_ghead_offset(int64_t m) { return (size_t)num_tiles(m) * kGradTileBytes; }
+__host__ __device__ inline size_t scratch_bytes(int64_t m) { return scratch_ghead_offset(m) + (size_t)num_tiles(m) * kTileM * 16; }
 
 // parameter slots in state_dict order
 enum ParamSlot {

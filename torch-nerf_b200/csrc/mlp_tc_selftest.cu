@@ -89,6 +89,62 @@ __global__ void __launch_bounds__(128, 1) selftest_umma_kernel(const uint16_t* _
   if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// micro-benchmark: sustained tcgen05.mma issue rate of one CTA per SM (M=128, K=16 per instruction)
+//   mode 0: A and B from shared memory (SS), N = n;   mode 1: A from TMEM (TS), B from shared memory
+// out[block] = cycles for `iters` groups of 4 MMAs (one 64-wide k-block), measured by the issuing thread.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, int n, int mode, unsigned long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  fence_proxy_async();
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = make_idesc_bf16((uint32_t)n, false, false);
+    const uint64_t da = desc_kmajor(smem_u32(smem));
+    const uint64_t db = desc_kmajor(smem_u32(smem) + 16384);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (mode == 0) umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, 1u);
+        else umma_bf16_ts(tmem_base, tmem_base + 256 + 8 * k, db + 2 * k, idesc, 1u);
+      }
+    }
+    umma_commit(&bar);
+    mbar_wait(&bar, 0);
+    const long long t1 = clock64();
+    out[blockIdx.x] = (unsigned long long)(t1 - t0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace nerf
 
 using namespace nerf;
@@ -103,6 +159,16 @@ int nerf_selftest_umma(const uint16_t* a_dev, const uint16_t* b_dev, float* d_de
   size_t smem = (size_t)128 * k * 2 + (size_t)n * k * 2 + 1024;
   NERF_CUDA(cudaFuncSetAttribute(selftest_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   selftest_umma_kernel<<<1, 128, smem, as_stream(stream)>>>(a_dev, b_dev, d_dev, n, k, variant);
+  NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
+
+int nerf_selftest_mma_rate(int blocks, int iters, int n, int mode, unsigned long long* cycles_dev, nerf_stream_t stream) {
+  NERF_CHECK_ARG(cycles_dev && blocks > 0 && iters > 0 && n >= 16 && n <= 256 && n % 16 == 0 && (mode == 0 || mode == 1),
+                 "nerf_selftest_mma_rate: bad arguments");
+  const size_t smem = 16384 + 32768 + 1024;
+  NERF_CUDA(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mma_rate_kernel<<<blocks, 128, smem, as_stream(stream)>>>(iters, n, mode, cycles_dev);
   NERF_LAUNCH_CHECK();
   return NERF_OK;
 }
