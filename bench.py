@@ -167,9 +167,9 @@ def run_b200(args):
     eng = HotPathEngine(coarse, fine, SC, SF, precision=args.precision)
     flat = eng.enable_flat_params()
     eng_render = eng if args.precision == "bf16" else HotPathEngine(coarse, fine, SC, SF, precision="bf16")
-    params = [p for net in (coarse, fine) for p in net.ordered_parameters()]
-    # runner_utils.py:690-711: Adam(lr 5e-4, eps 1e-8), ExponentialLR gamma = (5e-5/5e-4)^(1/300000)
-    opt = torch.optim.Adam(params, lr=5e-4, eps=1e-8, fused=True)
+    # runner_utils.py:690-711: Adam(lr 5e-4, eps 1e-8), ExponentialLR gamma = (5e-5/5e-4)^(1/300000); one Adam over both
+    # networks' parameters -- here as ONE flat parameter that all 44 tensors alias (elementwise-identical update)
+    opt = torch.optim.Adam([flat.param], lr=5e-4, eps=1e-8, fused=True)
     sched = torch.optim.lr_scheduler.ExponentialLR(opt, (5e-5 / 5e-4) ** (1.0 / 300000))
     torch.manual_seed(1234 + rank)  # per-rank uniform stream / pixels
     focal = blender_focal(IMG)

@@ -108,14 +108,18 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
     if (lane == 0) {
       uint32_t g = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint8_t* src = a.packed + kPackedBwdOff;
-        for (int c = 0; c < kBwdChunks; ++c) {
-          const uint32_t s = g % kDgStages, ph = (g / kDgStages) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full[s], kDgStageBytes);
-          bulk_g2s(sW + s * kDgStageBytes, src, kDgStageBytes, &full[s]);
-          src += kDgStageBytes;
-          ++g;
+        const uint8_t* layer_src = a.packed + kPackedBwdOff;
+        for (int j = 0; j < kNumBwdLayers; ++j) {
+          const int nk = bwd_nk(j);
+          for (int i = 0; i < nk; ++i) {
+            const int kb = nk == 4 ? kb_order(i) : i;
+            const uint32_t s = g % kDgStages, ph = (g / kDgStages) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_arrive_expect_tx(&full[s], kDgStageBytes);
+            bulk_g2s(sW + s * kDgStageBytes, layer_src + (size_t)kb * kDgStageBytes, kDgStageBytes, &full[s]);
+            ++g;
+          }
+          layer_src += (size_t)nk * kDgStageBytes;
         }
       }
     }
@@ -138,7 +142,8 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
             ++a_cnt[1];
           }
 #pragma unroll 1
-          for (int kb = 0; kb < nk; ++kb) {
+          for (int i = 0; i < nk; ++i) {
+            const int kb = nk == 4 ? kb_order(i) : i;
             if (j > 0) {
               mbar_wait(&a_ready[kb], a_cnt[kb] & 1);
               ++a_cnt[kb];
@@ -149,7 +154,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
             const uint64_t da = desc_kmajor(sA_u + kb * kBlockBytes);
             const uint64_t db = desc_kmajor(sW_u + s * kDgStageBytes);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
             umma_commit(&empty[s]);
             ++g;
           }
@@ -281,6 +286,7 @@ struct WUnit {
   int valid_cols;  // accumulator columns that map to real weight columns
   int param_b;     // bias slot or -1
   int b_off;
+  int cost;        // relative time per tile for the work partition (blocks streamed; more for CUDA-core-only units)
   int head;        // 0: none; 1: density head (d fc_8.weight[0,:], d fc_8.bias[0]) from g_sigma_pre and the X slices
                    // 2: fc_out (d fc_out.weight, d fc_out.bias) from gz and the X slices (X = h9, no MMA)
 };
@@ -308,9 +314,7 @@ struct Segment {
 };
 
 // cost-balanced contiguous partition of (unit, tile) pairs over the grid
-__device__ __forceinline__ int unit_cost(int u) {
-  return c_wunits[u].n_gblk + c_wunits[u].n_xblk + (c_wunits[u].x_extra >= 0 ? 1 : 0);
-}
+__device__ __forceinline__ int unit_cost(int u) { return c_wunits[u].cost; }
 
 __device__ inline int build_segments(int64_t ntiles, Segment* seg) {
   int64_t total = 0;
@@ -451,9 +455,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
     uint32_t g = 0;
     for (int si = 0; si < nseg; ++si) {
       const WUnit u = c_wunits[segs[si].unit];
-      const bool do_bias = u.param_b >= 0 && tid < u.n_gblk * 32;
-      const bool do_head = u.head != 0 && tid < u.n_xblk * 32;
-      const int col = 2 * tid;  // this thread's column pair, in G (bias) and in X (heads)
+      const bool do_bias = u.param_b >= 0 && tid < u.n_gblk * 32;  // (units with a bias have hsplit == 1)
+      // heads: 2 columns per thread; with fewer than 128 column pairs (fc_out: 64) the rows are split instead
+      const int head_pairs = u.n_xblk * 32;
+      const bool do_head = u.head != 0;
+      const int hsplit = (u.head != 0 && head_pairs < 128) ? 128 / head_pairs : 1;  // 1 or 2
+      const int hrows = 32 / hsplit;
+      const int hrow0 = (tid / (128 / hsplit)) * hrows;
+      const int col = 2 * (tid % (128 / hsplit));  // this thread's column pair, in G (bias) and in X (heads)
       const uint32_t coff = (uint32_t)(col >> 6) * kWgSlice + ((col & 63) & 7) * 2;
       const uint32_t chunk = (uint32_t)((col & 63) >> 3);
       float b0 = 0.f, b1 = 0.f;                                                 // bias column sums
@@ -478,7 +487,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
             if (do_head) {
               const uint8_t* xs = st + u.n_gblk * kWgSlice + coff;
 #pragma unroll 8
-              for (int r = 0; r < 32; ++r) {
+              for (int rr = 0; rr < hrows; ++rr) {
+                const int r = hrow0 + rr;
                 const uint32_t w = *reinterpret_cast<const uint32_t*>(xs + r * 128 + (((chunk ^ (uint32_t)(r & 7)) & 7u) << 4));
                 const float x0 = bf16_lo(w), x1 = bf16_hi(w);
                 const float4 gv = gh[r];
@@ -556,7 +566,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
 static void build_wunits(WUnit* u) {
   int n = 0;
   auto add = [&](int g0, int ng, int x0, int nx, int xe, int pw, int row0, int col0, int ld, int valid, int pb, int boff,
-                 int head) { u[n++] = WUnit{g0, ng, x0, nx, xe, pw, row0, col0, ld, valid, pb, boff, head}; };
+                 int head) {
+    const int cost = ng > 0 ? ng + nx + (xe >= 0 ? 1 : 0) : 5;  // fc_out streams 2 blocks but is CUDA-core bound
+    u[n++] = WUnit{g0, ng, x0, nx, xe, pw, row0, col0, ld, valid, pb, boff, cost, head};
+  };
   add(grad_g(0), 4, kCachePe, 1, -1, W_IN, 0, 0, kP, kP, B_IN, 0, 0);                      // fc_in : G0 x pe
   for (int l = 1; l <= 4; ++l) add(grad_g(l), 4, cache_h(l - 1), 4, -1, 2 * l, 0, 0, kF, kF, 2 * l + 1, 0, 0);  // fc_1..4
   add(grad_g(5), 4, kCachePe, 1, -1, W_5, 0, 0, kP + kF, kP, B_5, 0, 0);                   // fc_5, position columns

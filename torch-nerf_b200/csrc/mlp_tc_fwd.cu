@@ -27,6 +27,13 @@
 namespace nerf {
 using namespace tc;
 
+// i-th weight chunk (= k-block of the layer's K dimension) consumed by layer l.  4-block layers follow kb_order;
+// the 5-block layers put the block that does not depend on the previous epilogue first (fc_5: encoded position,
+// chunk 0) or keep it last (fc_9: encoded view direction, chunk 4).
+__host__ __device__ constexpr int fwd_chunk(int l, int i) {
+  return fwd_nk(l) == 4 ? kb_order(i) : (l == 5 ? (i == 0 ? 0 : 1 + kb_order(i - 1)) : (l == 9 ? (i < 4 ? kb_order(i) : 4) : i));
+}
+
 constexpr int kStages = 3;
 constexpr int kStageBytes = 32768;
 constexpr int kFwdThreads = 320;
@@ -166,17 +173,19 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
     if (lane == 0) {
       uint32_t g = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint8_t* src = a.packed + kPackedFwdOff;
+        const uint8_t* layer_src = a.packed + kPackedFwdOff;
         for (int l = 0; l < kNumFwdLayers; ++l) {
           const uint32_t bytes = fwd_n(l) * 128;
-          for (int kb = 0; kb < fwd_nk(l); ++kb) {
+          const int nk = fwd_nk(l);
+          for (int i = 0; i < nk; ++i) {
+            const int kb = fwd_chunk(l, i);
             const uint32_t s = g % kStages, ph = (g / kStages) & 1;
             mbar_wait(&empty[s], ph ^ 1);
             mbar_arrive_expect_tx(&full[s], bytes);
-            bulk_g2s(sW + s * kStageBytes, src, bytes, &full[s]);
-            src += bytes;
+            bulk_g2s(sW + s * kStageBytes, layer_src + (size_t)kb * bytes, bytes, &full[s]);
             ++g;
           }
+          layer_src += (size_t)nk * bytes;
         }
       }
     }
@@ -196,7 +205,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
           const int nk = fwd_nk(l);
           const bool stamp = a.prof != nullptr && blockIdx.x == 0 && (int)in_cnt <= a.prof_tiles;
           if (stamp) a.prof[(((int)in_cnt - 1) * kNumFwdLayers + l) * 4 + 0] = clock64();
-          for (int kb = 0; kb < nk; ++kb) {
+          for (int i = 0; i < nk; ++i) {
+            const int kb = fwd_chunk(l, i);
             uint32_t a_addr;
             int nsteps = 4;
             if (l == 0 || (l == 5 && kb == 0)) {
@@ -216,7 +226,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
             const uint64_t da = desc_kmajor(a_addr);
             const uint64_t db = desc_kmajor(sW_u + s * kStageBytes);
 #pragma unroll 4
-            for (int k = 0; k < nsteps; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < nsteps; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
             umma_commit(&empty[s]);
             ++g;
           }

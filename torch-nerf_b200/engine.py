@@ -42,6 +42,9 @@ class FlatParams:
             self.grad_views.append(g)
             off += n
         self.per_net = len(params) // len(self.nets)
+        # one Parameter over the whole buffer: an optimizer stepping it updates every network parameter (they alias it)
+        self.param = torch.nn.Parameter(self.flat, requires_grad=True)
+        self.param.grad = self.grad
 
     def grads_of(self, i: int):
         return self.grad_views[i * self.per_net:(i + 1) * self.per_net]
@@ -128,7 +131,9 @@ class HotPathEngine:
             self._call("nerf_mlp_f32_forward", net._dims, params, P(pe), P(de), m, P(sigma), P(rad), P(cache), st, launches=16)
             ctx["cache"] = cache
         else:
-            packed = net.packed_weights()
+            # with flat parameters an optimizer may have stepped the shared buffer without touching the per-tensor
+            # version counters, so the bf16 image is rebuilt on every pass (2.3 MB, ~10 us)
+            packed = net.packed_weights(force=train or self.flat is not None)
             cache = None
             if train:
                 cache = self._get(tag + "cache16", (self.lib.nerf_mlp_bf16_cache_bytes(m),), torch.uint8)

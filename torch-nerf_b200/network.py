@@ -166,12 +166,14 @@ class NeRF(nn.Module):
     def supports_bf16(self) -> bool:
         return (self._pos_dim, self._view_dir_dim, self._feat_dim) == (63, 27, 256)
 
-    def packed_weights(self) -> torch.Tensor:
-        """bf16 swizzled weight image for the tcgen05 chain, re-packed whenever a parameter changed."""
+    def packed_weights(self, force: bool = False) -> torch.Tensor:
+        """bf16 swizzled weight image for the tcgen05 chains, re-packed whenever a parameter changed (tracked through
+        the parameters' version counters) or when `force` is set (e.g. after an optimizer stepped a flat buffer the
+        parameters alias)."""
         lib = _lib.load()
         params = self.ordered_parameters()
         version = tuple(p._version for p in params) + tuple(p.data_ptr() for p in params)
-        if self._packed is None or self._packed_version != version:
+        if force or self._packed is None or self._packed_version != version:
             dev = params[0].device
             if self._packed is None or self._packed.device != dev:
                 self._packed = torch.empty((lib.nerf_mlp_bf16_packed_bytes(),), device=dev, dtype=torch.uint8)
