@@ -158,7 +158,41 @@ def test_engine_training_converges_bf16_like_fp32(tn):
             losses = eng.train_pixels(cam, pix, tgt, False)
             opt.step()
             hist.append(float(losses.sum()))
-        final[precision] = (hist[0], min(hist[-5:]))
+        final[precision] = (hist[0], min(hist[-5:]), [round(h, 4) for h in hist[::4]])
     assert final["fp32"][1] < 0.7 * final["fp32"][0], final
     assert final["bf16"][1] < 0.7 * final["bf16"][0], final
     assert final["bf16"][1] < 1.5 * final["fp32"][1] + 1e-3, final
+
+
+@pytest.mark.parametrize("n", [1024, 4096])
+def test_engine_bf16_grads_match_fp32_at_scale(tn, n):
+    """Same rays, same uniforms, both precisions: every gradient tensor of the tensor-core step must point the same
+    way as the fp32-validation step (many tiles per CTA, every wgrad segment shape)."""
+    from torch_nerf_b200.engine import HotPathEngine
+
+    g = load_golden("train_step.npz")
+    cam = camera(tn, g)
+    gen = torch.Generator().manual_seed(n)
+    pix = torch.randperm(800 * 800, generator=gen)[:n].cuda()
+    tgt = torch.rand((n, 3), generator=gen).cuda()
+    u = tuple(torch.rand((n, k), generator=gen).cuda() for k in (64, 64, 128, 128))
+    grads = {}
+    for precision in ("fp32", "bf16"):
+        coarse, fine = nets(tn, 71, 72, precision)
+        eng = HotPathEngine(coarse, fine, 64, 128, precision=precision)
+        losses = eng.train_pixels(cam, pix, tgt, False, uniforms=u)
+        torch.cuda.synchronize()
+        grads[precision] = ({k: p.grad.clone() for k, p in coarse.named_parameters()},
+                            {k: p.grad.clone() for k, p in fine.named_parameters()}, losses.clone())
+    np.testing.assert_allclose(grads["bf16"][2].cpu().numpy(), grads["fp32"][2].cpu().numpy(), rtol=2e-2)
+    report = []
+    for which, tag in ((0, "c/"), (1, "f/")):
+        for k in grads["fp32"][which]:
+            a, b = grads["fp32"][which][k].reshape(-1).double(), grads["bf16"][which][k].reshape(-1).double()
+            cos = float((a * b).sum() / (a.norm() * b.norm() + 1e-30))
+            ratio = float(b.norm() / (a.norm() + 1e-30))
+            report.append((tag + k, cos, ratio))
+    # the coarse network sees identical samples in both runs; the fine pass resamples from slightly different
+    # coarse weights, so its gradients agree a little less
+    bad = [r for r in report if r[1] < (0.98 if r[0].startswith("c/") else 0.95) or abs(r[2] - 1) > 0.15]
+    assert not bad, "\n".join(f"{k}: cos {c:.4f} norm ratio {r:.3f}" for k, c, r in report)
