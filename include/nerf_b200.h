@@ -185,8 +185,9 @@ int nerf_selftest_umma(const uint16_t* a_dev, const uint16_t* b_dev, float* d_de
                        nerf_stream_t stream);
 
 /* debugging aid: when buf_dev != NULL, CTA 0 of the next nerf_mlp_bf16_forward launches records, for its first
- * `tiles` tiles and every layer, 4 SM-clock stamps (MMA layer start, MMA layer issued, accumulator seen by the
- * epilogue, epilogue done) into buf_dev[(tile*10 + layer)*4 + k].  Pass NULL to switch it off. */
+ * `tiles` tiles and every layer, 8 values into buf_dev[(tile*10 + layer)*8 + k]: SM-clock stamps k=0 MMA layer
+ * start, 1 MMA layer issued, 2 accumulator seen by the epilogue, 3 epilogue done; cycle sums k=4 MMA thread waiting
+ * for activations, 5 waiting for weights.  Pass NULL to switch it off. */
 int nerf_debug_set_profile_buffer(unsigned long long* buf_dev, int tiles);
 
 /* micro-benchmark: `blocks` CTAs each issue `iters` x 4 tcgen05.mma (M=128, N=n, K=16); cycles_dev[block] = SM cycles.

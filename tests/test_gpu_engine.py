@@ -136,32 +136,32 @@ def test_engine_train_step_bf16_vs_golden(tn):
     assert not bad, "\n".join(f"{k}: cos {c:.4f} abssum ratio {r:.3f}" for k, c, r in report)
 
 
-def test_engine_training_converges_bf16_like_fp32(tn):
-    """40 Adam steps on one fixed 1024-ray batch: the tensor-core path must drive the loss down like the fp32 path."""
+def test_engine_training_tracks_fp32(tn):
+    """Adam steps on one fixed 1024-ray batch: the tensor-core path must follow the fp32 path's loss curve step by
+    step.  (Only the first steps are compared: with the reference's 1e8 last interval the dynamics are chaotic --
+    |g_sigma| ~ 1e5 outliers make either precision occasionally collapse to the transparent solution, see DESIGN.md.)"""
     from torch_nerf_b200.engine import HotPathEngine
 
     g = load_golden("train_step.npz")
     cam = camera(tn, g)
     gen = torch.Generator().manual_seed(5)
     pix = torch.randperm(800 * 800, generator=gen)[:1024].cuda()
-    # a smooth synthetic target (function of the pixel position) so there is something to fit
     tgt = torch.stack([(pix % 800).float() / 800, (pix // 800).float() / 800, torch.full((1024,), 0.5, device="cuda")], -1).contiguous()
-    final = {}
+    hist = {}
     for precision in ("fp32", "bf16"):
         coarse, fine = nets(tn, 61, 62, precision)
         eng = HotPathEngine(coarse, fine, 64, 128, precision=precision)
-        eng.enable_flat_params()
-        opt = torch.optim.Adam([p for n_ in (coarse, fine) for p in n_.ordered_parameters()], lr=5e-4, eps=1e-8)
+        flat = eng.enable_flat_params()
+        opt = torch.optim.Adam([flat.param], lr=5e-4, eps=1e-8)
         torch.manual_seed(11)
-        hist = []
-        for it in range(40):
+        hist[precision] = []
+        for it in range(12):
             losses = eng.train_pixels(cam, pix, tgt, False)
             opt.step()
-            hist.append(float(losses.sum()))
-        final[precision] = (hist[0], min(hist[-5:]), [round(h, 4) for h in hist[::4]])
-    assert final["fp32"][1] < 0.7 * final["fp32"][0], final
-    assert final["bf16"][1] < 0.7 * final["bf16"][0], final
-    assert final["bf16"][1] < 1.5 * final["fp32"][1] + 1e-3, final
+            hist[precision].append(float(losses.sum()))
+    a, b = np.array(hist["fp32"]), np.array(hist["bf16"])
+    assert a[-1] < 0.85 * a[0], hist
+    np.testing.assert_allclose(b, a, rtol=3e-2, err_msg=str(hist))
 
 
 @pytest.mark.parametrize("n", [1024, 4096])

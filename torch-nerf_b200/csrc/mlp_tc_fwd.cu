@@ -204,7 +204,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
           const uint32_t idesc = (l == 9) ? idesc128 : idesc256;
           const int nk = fwd_nk(l);
           const bool stamp = a.prof != nullptr && blockIdx.x == 0 && (int)in_cnt <= a.prof_tiles;
-          if (stamp) a.prof[(((int)in_cnt - 1) * kNumFwdLayers + l) * 4 + 0] = clock64();
+          if (stamp) a.prof[(((int)in_cnt - 1) * kNumFwdLayers + l) * 8 + 0] = clock64();
+          long long wait_a = 0, wait_w = 0;
           for (int i = 0; i < nk; ++i) {
             const int kb = fwd_chunk(l, i);
             uint32_t a_addr;
@@ -217,11 +218,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
             } else {
               const int ab = (l == 5) ? kb - 1 : kb;
               // a_ready[ab] completes once per producing layer 0..8; layer l consumes round (l - 1)
+              const long long w0 = stamp ? clock64() : 0;
               mbar_wait(&a_ready[ab], (a_cnt + (uint32_t)(l - 1)) & 1);
+              if (stamp) wait_a += clock64() - w0;
               a_addr = sA_u + ab * kBlockBytes;
             }
             const uint32_t s = g % kStages, ph = (g / kStages) & 1;
+            const long long w1 = stamp ? clock64() : 0;
             mbar_wait(&full[s], ph);
+            if (stamp) wait_w += clock64() - w1;
             tc_fence_after();
             const uint64_t da = desc_kmajor(a_addr);
             const uint64_t db = desc_kmajor(sW_u + s * kStageBytes);
@@ -231,7 +236,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
             ++g;
           }
           umma_commit(&acc_full[l & 1]);
-          if (stamp) a.prof[(((int)in_cnt - 1) * kNumFwdLayers + l) * 4 + 1] = clock64();
+          if (stamp) {
+            unsigned long long* pr = a.prof + (((int)in_cnt - 1) * kNumFwdLayers + l) * 8;
+            pr[1] = clock64();
+            pr[4] = (unsigned long long)wait_a;
+            pr[5] = (unsigned long long)wait_w;
+          }
         }
         a_cnt += 9;
       }
@@ -301,7 +311,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
           ++accn0;
         }
         tc_fence_after();
-        if (stamp) a.prof[((tile_iter * kNumFwdLayers + l) * 4) + 2] = clock64();
+        if (stamp) a.prof[((tile_iter * kNumFwdLayers + l) * 8) + 2] = clock64();
         const uint32_t taddr = lane_addr + (uint32_t)(l & 1) * 256u;
         const float* bias = sC + ((l < 8) ? kCBias + 256 * l : (l == 8 ? kCBias8 : kCBias9));
         if (l < 9) {
@@ -347,7 +357,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
             mbar_arrive(&a_ready[kb]);
           }
           if (l == 7 && half == 1) sX[row * 4 + 3] = sigma_part;
-          if (stamp) a.prof[((tile_iter * kNumFwdLayers + l) * 4) + 3] = clock64();
+          if (stamp) a.prof[((tile_iter * kNumFwdLayers + l) * 8) + 3] = clock64();
         } else {
           // fc_9 output (128 columns): this half owns columns [64*half, 64*half + 64)
           uint32_t v0[32], v1[32];
@@ -406,7 +416,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
             }
             if (kTrain) mask_tile[kMaskSigmaWord * kTileM + row] = (grow < a.m && sp > 0.f) ? 1u : 0u;
           }
-          if (stamp) a.prof[((tile_iter * kNumFwdLayers + l) * 4) + 3] = clock64();
+          if (stamp) a.prof[((tile_iter * kNumFwdLayers + l) * 8) + 3] = clock64();
         }
       }
     }
