@@ -27,8 +27,8 @@ using namespace tc;
 // ================================================================================================
 // 1. dgrad chain
 // ================================================================================================
-constexpr int kDgStages = 8;
-constexpr int kDgStageBytes = kChunkBytes;  // 128 input features x 64 output features
+constexpr int kDgStages = 4;
+constexpr int kDgStageBytes = 32768;
 constexpr int kDgThreads = 320;
 constexpr int kDgEpiThreads = 256;
 constexpr int kDgSmA = 0;
@@ -48,14 +48,13 @@ struct DgradArgs {
   int64_t m;
 };
 
-// `neg` holds the sign bits of the forward pre-activations, column i at bit (31 - i): set = ReLU was inactive
-__device__ __forceinline__ void masked_group(const uint32_t (&v)[32], uint32_t neg, float add_scale,
+__device__ __forceinline__ void masked_group(const uint32_t (&v)[32], uint32_t mask, float add_scale,
                                              const float* __restrict__ add_vec, float (&f)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
     float t = __uint_as_float(v[i]);
     if (add_vec != nullptr) t = fmaf(add_scale, add_vec[i], t);
-    f[i] = ((neg >> (31 - i)) & 1u) ? 0.f : t;
+    f[i] = ((mask >> i) & 1u) ? t : 0.f;
   }
 }
 
@@ -78,8 +77,8 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
   uint64_t* full = bars;
   uint64_t* empty = bars + kDgStages;
   uint64_t* a_ready = bars + 2 * kDgStages;  // [4]
-  uint64_t* acc_full = a_ready + 4;          // [2 accumulators][2 N-halves]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 4);
+  uint64_t* acc_full = a_ready + 4;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ntiles = num_tiles(a.m);
@@ -93,7 +92,8 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], 128);
-    for (int i = 0; i < 4; ++i) mbar_init(&acc_full[i], 1);
+    mbar_init(&acc_full[0], 1);
+    mbar_init(&acc_full[1], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -108,14 +108,18 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
     if (lane == 0) {
       uint32_t g = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint8_t* src = a.packed + kPackedBwdOff;
-        for (int c = 0; c < kBwdChunks; ++c) {
-          const uint32_t s = g % kDgStages, ph = (g / kDgStages) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full[s], kDgStageBytes);
-          bulk_g2s(sW + s * kDgStageBytes, src, kDgStageBytes, &full[s]);
-          src += kDgStageBytes;
-          ++g;
+        const uint8_t* layer_src = a.packed + kPackedBwdOff;
+        for (int j = 0; j < kNumBwdLayers; ++j) {
+          const int nk = bwd_nk(j);
+          for (int i = 0; i < nk; ++i) {
+            const int kb = nk == 4 ? kb_order(i) : i;
+            const uint32_t s = g % kDgStages, ph = (g / kDgStages) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_arrive_expect_tx(&full[s], kDgStageBytes);
+            bulk_g2s(sW + s * kDgStageBytes, layer_src + (size_t)kb * kDgStageBytes, kDgStageBytes, &full[s]);
+            ++g;
+          }
+          layer_src += (size_t)nk * kDgStageBytes;
         }
       }
     }
@@ -123,39 +127,38 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
     if (lane == 0) {
       uint32_t g = 0;
       uint32_t a_cnt[4] = {0, 0, 0, 0};
-      constexpr uint32_t idesc = make_idesc_bf16(128, false, false);
+      constexpr uint32_t idesc = make_idesc_bf16(256, false, false);
       const uint32_t sA_u = smem_u32(sA), sW_u = smem_u32(sW);
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int j = 0; j < kNumBwdLayers; ++j) {
+          const uint32_t acc = tmem_base + (uint32_t)(j & 1) * 256u;
           const int nk = bwd_nk(j);
           if (j == 0) {
-            // both warp groups must have left the previous tile's last epilogue (they read accumulator 0, which
-            // this layer overwrites) -- each group signals its G9 block only after that
+            // both column halves must have left the previous tile's last epilogue (they read accumulator 0, which
+            // this layer overwrites) -- each half signals its G9 block only after that
             mbar_wait(&a_ready[0], a_cnt[0] & 1);
             mbar_wait(&a_ready[1], a_cnt[1] & 1);
             ++a_cnt[0];
             ++a_cnt[1];
           }
-          for (int nh = 0; nh < 2; ++nh) {
-            const uint32_t acc = tmem_base + (uint32_t)(j & 1) * 256u + (uint32_t)nh * 128u;
 #pragma unroll 1
-            for (int kb = 0; kb < nk; ++kb) {
-              if (j > 0 && nh == 0) {
-                mbar_wait(&a_ready[kb], a_cnt[kb] & 1);
-                ++a_cnt[kb];
-              }
-              const uint32_t s = g % kDgStages, ph = (g / kDgStages) & 1;
-              mbar_wait(&full[s], ph);
-              tc_fence_after();
-              const uint64_t da = desc_kmajor(sA_u + kb * kBlockBytes);
-              const uint64_t db = desc_kmajor(sW_u + s * kDgStageBytes);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-              umma_commit(&empty[s]);
-              ++g;
+          for (int i = 0; i < nk; ++i) {
+            const int kb = nk == 4 ? kb_order(i) : i;
+            if (j > 0) {
+              mbar_wait(&a_ready[kb], a_cnt[kb] & 1);
+              ++a_cnt[kb];
             }
-            umma_commit(&acc_full[(j & 1) * 2 + nh]);
+            const uint32_t s = g % kDgStages, ph = (g / kDgStages) & 1;
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint64_t da = desc_kmajor(sA_u + kb * kBlockBytes);
+            const uint64_t db = desc_kmajor(sW_u + s * kDgStageBytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&empty[s]);
+            ++g;
           }
+          umma_commit(&acc_full[j & 1]);
         }
       }
     }
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
     const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t accn[4] = {0, 0, 0, 0};
+    uint32_t accn0 = 0, accn1 = 0;
     uint8_t* a_row = sA + row * 128;
     float4* ghead_out = reinterpret_cast<float4*>(a.scratch + scratch_ghead_offset(a.m));
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
             float t = gz0 * sWout[col0 + i];
             t = fmaf(gz1, sWout[128 + col0 + i], t);
             t = fmaf(gz2, sWout[256 + col0 + i], t);
-            f[i] = ((mk >> (31 - i)) & 1u) ? 0.f : t;
+            f[i] = ((mk >> i) & 1u) ? t : 0.f;
           }
           store_group_bf16(f, a_row + half * kBlockBytes, row, gi * 4);
         }
@@ -210,19 +213,23 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
         mbar_arrive(&a_ready[half]);
       }
       for (int j = 0; j < kNumBwdLayers; ++j) {
+        if (j & 1) {
+          mbar_wait(&acc_full[1], accn1 & 1);
+          ++accn1;
+        } else {
+          mbar_wait(&acc_full[0], accn0 & 1);
+          ++accn0;
+        }
+        tc_fence_after();
         const uint32_t taddr = lane_addr + (uint32_t)(j & 1) * 256u;
         const int slot = 8 - j;  // ReLU mask of the layer output this gradient flows into (j >= 1): h7 .. h0
 #pragma unroll 1
         for (int t = 0; t < 2; ++t) {
-          const int kb = half + 2 * t;  // N-half t, this warp group's 64 columns of it
-          const int bi = (j & 1) * 2 + t;
-          mbar_wait(&acc_full[bi], accn[bi] & 1);
-          ++accn[bi];
-          tc_fence_after();
+          const int kb = half + 2 * t;
           uint32_t v0[32], v1[32];
           tmem_ld32(taddr + kb * 64, v0);
           tmem_ld32(taddr + kb * 64 + 32, v1);
-          uint32_t m0 = 0u, m1 = 0u;  // sign-bit masks: 0 = every column passes (layer j = 0 has no ReLU)
+          uint32_t m0 = 0xffffffffu, m1 = 0xffffffffu;
           if (j >= 1) {
             m0 = __ldg(mask_tile + (slot * 8 + 2 * kb) * kTileM + row);
             m1 = __ldg(mask_tile + (slot * 8 + 2 * kb + 1) * kTileM + row);

@@ -1,15 +1,14 @@
 // K4+K5 on the sm_100a tensor cores: the NeRF MLP forward (network/nerf.py:65-121) as a chain of tcgen05 BF16 MMAs
 // with fp32 accumulation in TMEM; positional encoding (signal_encoder/positional_encoder.py:49-104, as applied by
 // scene/primitives/cube.py:62-69) is computed in-kernel as the first layer's operand; weights are streamed from L2
-// by the TMA engine (cp.async.bulk + mbarrier) through a 6-stage ring of 16 KB chunks.
+// by the TMA engine (cp.async.bulk + mbarrier) through a 3-stage ring.
 //
 // One CTA per SM, 128 sample rows per tile, activations never leave the SM (inference).  In training mode the
 // kernel additionally writes every layer input as a tile image plus ReLU bit masks into the training cache.
 //
 //   warp 0      weight loader   1-D bulk copies of pre-swizzled bf16 weight chunks (N x 64)
-//   warp 1      MMA issuer      one thread issues tcgen05.mma (M=128, N=128, K=16).  A 256-wide layer is two N-halves
-//                               committed separately, so output columns [0,128) are drained while the tensor pipe
-//                               computes [128,256); accumulators ping-pong between TMEM columns [0,256) / [256,512)
+//   warp 1      MMA issuer      one thread issues tcgen05.mma (M=128, N=256|128, K=16); accumulators ping-pong
+//                               between TMEM columns [0,256) and [256,512) from layer to layer
 //   warps 2-9   epilogue        two warps per TMEM lane quarter (column halves): tcgen05.ld -> +bias, ReLU -> bf16
 //                               -> swizzled smem = next layer's A operand, signalled per 64-column k-block so the
 //                               next layer's MMAs start while the rest of the accumulator is still being drained;
@@ -28,8 +27,15 @@
 namespace nerf {
 using namespace tc;
 
-constexpr int kStages = 6;
-constexpr int kStageBytes = kChunkBytes;  // 128 output rows x 64 K-columns
+// i-th weight chunk (= k-block of the layer's K dimension) consumed by layer l.  4-block layers follow kb_order;
+// the 5-block layers put the block that does not depend on the previous epilogue first (fc_5: encoded position,
+// chunk 0) or keep it last (fc_9: encoded view direction, chunk 4).
+__host__ __device__ constexpr int fwd_chunk(int l, int i) {
+  return fwd_nk(l) == 4 ? kb_order(i) : (l == 5 ? (i == 0 ? 0 : 1 + kb_order(i - 1)) : (l == 9 ? (i < 4 ? kb_order(i) : 4) : i));
+}
+
+constexpr int kStages = 3;
+constexpr int kStageBytes = 32768;
 constexpr int kFwdThreads = 320;
 constexpr int kEpiThreads = 256;
 // shared memory map (bytes from the 1024-aligned base)
@@ -90,27 +96,26 @@ __device__ __forceinline__ void encode_row(float x, float y, float z, uint8_t* r
   }
 }
 
-// 32 accumulator columns -> +bias -> (ReLU).  Returns the sign bits of the pre-activations, element i at bit
-// (31 - i): one funnel shift per element (the training cache's ReLU mask, see mlp_tc_layout.cuh).
+// 32 accumulator columns -> +bias -> (ReLU) -> bf16 -> four 16-byte chunks of the A operand row
 template <bool RELU>
-__device__ __forceinline__ uint32_t finish_group(const uint32_t (&v)[32], const float* __restrict__ bias, float (&f)[32]) {
-  uint32_t neg = 0;
+__device__ __forceinline__ void finish_group(const uint32_t (&v)[32], const float* __restrict__ bias, float (&f)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; i += 4) {
     const float4 b = *reinterpret_cast<const float4*>(bias + i);
-    const float t[4] = {__uint_as_float(v[i]) + b.x, __uint_as_float(v[i + 1]) + b.y, __uint_as_float(v[i + 2]) + b.z,
-                        __uint_as_float(v[i + 3]) + b.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      if (RELU) {
-        neg = __funnelshift_l(__float_as_uint(t[e]), neg, 1);
-        f[i + e] = fmaxf(t[e], 0.f);
-      } else {
-        f[i + e] = t[e];
-      }
+    float t0 = __uint_as_float(v[i]) + b.x, t1 = __uint_as_float(v[i + 1]) + b.y;
+    float t2 = __uint_as_float(v[i + 2]) + b.z, t3 = __uint_as_float(v[i + 3]) + b.w;
+    if (RELU) {
+      t0 = fmaxf(t0, 0.f), t1 = fmaxf(t1, 0.f), t2 = fmaxf(t2, 0.f), t3 = fmaxf(t3, 0.f);
     }
+    f[i] = t0, f[i + 1] = t1, f[i + 2] = t2, f[i + 3] = t3;
   }
-  return neg;
+}
+
+__device__ __forceinline__ uint32_t relu_mask(const float (&f)[32]) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) m |= (f[i] > 0.f ? 1u : 0u) << i;
+  return m;
 }
 
 __device__ __forceinline__ void store_group(const float (&f)[32], uint8_t* blk_row, int row, int chunk0) {
@@ -136,8 +141,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
   uint64_t* empty = bars + kStages;        // [kStages]
   uint64_t* a_ready = bars + 2 * kStages;  // [4]   one completion per producing layer
   uint64_t* in_ready = a_ready + 4;        // [1]   one completion per tile
-  uint64_t* acc_full = in_ready + 1;       // [2 accumulators][2 N-halves]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 4);
+  uint64_t* acc_full = in_ready + 1;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ntiles = num_tiles(a.m);
@@ -153,7 +158,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
     }
     for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], 128);
     mbar_init(in_ready, kEpiThreads);
-    for (int i = 0; i < 4; ++i) mbar_init(&acc_full[i], 1);
+    mbar_init(&acc_full[0], 1);
+    mbar_init(&acc_full[1], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -167,14 +173,19 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
     if (lane == 0) {
       uint32_t g = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint8_t* src = a.packed + kPackedFwdOff;
-        for (int c = 0; c < kFwdChunks; ++c) {
-          const uint32_t s = g % kStages, ph = (g / kStages) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full[s], kStageBytes);
-          bulk_g2s(sW + s * kStageBytes, src, kStageBytes, &full[s]);
-          src += kStageBytes;
-          ++g;
+        const uint8_t* layer_src = a.packed + kPackedFwdOff;
+        for (int l = 0; l < kNumFwdLayers; ++l) {
+          const uint32_t bytes = fwd_n(l) * 128;
+          const int nk = fwd_nk(l);
+          for (int i = 0; i < nk; ++i) {
+            const int kb = fwd_chunk(l, i);
+            const uint32_t s = g % kStages, ph = (g / kStages) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_arrive_expect_tx(&full[s], bytes);
+            bulk_g2s(sW + s * kStageBytes, layer_src + (size_t)kb * bytes, bytes, &full[s]);
+            ++g;
+          }
+          layer_src += (size_t)nk * bytes;
         }
       }
     }
@@ -182,50 +193,49 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       uint32_t g = 0, a_cnt = 0, in_cnt = 0;
-      constexpr uint32_t idesc = make_idesc_bf16(128, false, false);
+      constexpr uint32_t idesc256 = make_idesc_bf16(256, false, false);
+      constexpr uint32_t idesc128 = make_idesc_bf16(128, false, false);
       const uint32_t sA_u = smem_u32(sA), sIn_u = smem_u32(sIn), sW_u = smem_u32(sW);
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         mbar_wait(in_ready, in_cnt & 1);
         ++in_cnt;
         for (int l = 0; l < kNumFwdLayers; ++l) {
+          const uint32_t acc = tmem_base + (uint32_t)(l & 1) * 256u;
+          const uint32_t idesc = (l == 9) ? idesc128 : idesc256;
           const int nk = fwd_nk(l);
           const bool stamp = a.prof != nullptr && blockIdx.x == 0 && (int)in_cnt <= a.prof_tiles;
           if (stamp) a.prof[(((int)in_cnt - 1) * kNumFwdLayers + l) * 8 + 0] = clock64();
           long long wait_a = 0, wait_w = 0;
-          for (int nh = 0; nh < fwd_nh(l); ++nh) {
-            const uint32_t acc = tmem_base + (uint32_t)(l & 1) * 256u + (uint32_t)nh * 128u;
-            for (int kb = 0; kb < nk; ++kb) {
-              uint32_t a_addr;
-              int nsteps = 4;
-              if (l == 0 || (l == 5 && kb == 0)) {
-                a_addr = sIn_u;                      // encoded position
-              } else if (l == 9 && kb == 4) {
-                a_addr = sIn_u + kBlockBytes;        // encoded view direction (K = 32)
-                nsteps = 2;
-              } else {
-                const int ab = (l == 5) ? kb - 1 : kb;
-                if (nh == 0) {
-                  // a_ready[ab] completes once per producing layer 0..8; layer l consumes round (l - 1)
-                  const long long w0 = stamp ? clock64() : 0;
-                  mbar_wait(&a_ready[ab], (a_cnt + (uint32_t)(l - 1)) & 1);
-                  if (stamp) wait_a += clock64() - w0;
-                }
-                a_addr = sA_u + ab * kBlockBytes;
-              }
-              const uint32_t s = g % kStages, ph = (g / kStages) & 1;
-              const long long w1 = stamp ? clock64() : 0;
-              mbar_wait(&full[s], ph);
-              if (stamp) wait_w += clock64() - w1;
-              tc_fence_after();
-              const uint64_t da = desc_kmajor(a_addr);
-              const uint64_t db = desc_kmajor(sW_u + s * kStageBytes);
-#pragma unroll 4
-              for (int k = 0; k < nsteps; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-              umma_commit(&empty[s]);
-              ++g;
+          for (int i = 0; i < nk; ++i) {
+            const int kb = fwd_chunk(l, i);
+            uint32_t a_addr;
+            int nsteps = 4;
+            if (l == 0 || (l == 5 && kb == 0)) {
+              a_addr = sIn_u;                      // encoded position
+            } else if (l == 9 && kb == 4) {
+              a_addr = sIn_u + kBlockBytes;        // encoded view direction (K = 32)
+              nsteps = 2;
+            } else {
+              const int ab = (l == 5) ? kb - 1 : kb;
+              // a_ready[ab] completes once per producing layer 0..8; layer l consumes round (l - 1)
+              const long long w0 = stamp ? clock64() : 0;
+              mbar_wait(&a_ready[ab], (a_cnt + (uint32_t)(l - 1)) & 1);
+              if (stamp) wait_a += clock64() - w0;
+              a_addr = sA_u + ab * kBlockBytes;
             }
-            umma_commit(&acc_full[(l & 1) * 2 + nh]);
+            const uint32_t s = g % kStages, ph = (g / kStages) & 1;
+            const long long w1 = stamp ? clock64() : 0;
+            mbar_wait(&full[s], ph);
+            if (stamp) wait_w += clock64() - w1;
+            tc_fence_after();
+            const uint64_t da = desc_kmajor(a_addr);
+            const uint64_t db = desc_kmajor(sW_u + s * kStageBytes);
+#pragma unroll 4
+            for (int k = 0; k < nsteps; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&empty[s]);
+            ++g;
           }
+          umma_commit(&acc_full[l & 1]);
           if (stamp) {
             unsigned long long* pr = a.prof + (((int)in_cnt - 1) * kNumFwdLayers + l) * 8;
             pr[1] = clock64();
@@ -239,10 +249,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
   } else {
     // ------------------------------------------------------------------ epilogue warps
     const int q = warp & 3;             // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;   // warp group: drains k-block `half` of N-half 0 and k-block `2 + half` of N-half 1
+    const int half = (warp - 2) >> 2;   // column half: k-blocks {half, half + 2}
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t accn[4] = {0, 0, 0, 0};  // completions seen per (accumulator, N-half) barrier
+    uint32_t accn0 = 0, accn1 = 0;
     uint8_t* a_row = sA + row * 128;
     int tile_iter = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_iter) {
@@ -293,18 +303,21 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
       float sigma_part = 0.f;
       float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
       for (int l = 0; l < kNumFwdLayers; ++l) {
+        if (l & 1) {
+          mbar_wait(&acc_full[1], accn1 & 1);
+          ++accn1;
+        } else {
+          mbar_wait(&acc_full[0], accn0 & 1);
+          ++accn0;
+        }
+        tc_fence_after();
+        if (stamp) a.prof[((tile_iter * kNumFwdLayers + l) * 8) + 2] = clock64();
         const uint32_t taddr = lane_addr + (uint32_t)(l & 1) * 256u;
         const float* bias = sC + ((l < 8) ? kCBias + 256 * l : (l == 8 ? kCBias8 : kCBias9));
         if (l < 9) {
 #pragma unroll 1
           for (int t = 0; t < 2; ++t) {
-            // N-half t of the layer is complete: this warp drains block kb = 2t + half (64 of its 128 columns)
             const int kb = half + 2 * t;
-            const int bi = (l & 1) * 2 + t;
-            mbar_wait(&acc_full[bi], accn[bi] & 1);
-            ++accn[bi];
-            tc_fence_after();
-            if (stamp && t == 0) a.prof[((tile_iter * kNumFwdLayers + l) * 8) + 2] = clock64();
             uint32_t v0[32], v1[32];
             tmem_ld32(taddr + kb * 64, v0);
             tmem_ld32(taddr + kb * 64 + 32, v1);
@@ -315,22 +328,21 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
             tmem_ld_wait();
             uint8_t* blk_row = a_row + kb * kBlockBytes;
             float f[32];
-            uint32_t neg;
-            if (l == 8) neg = finish_group<false>(v0, bias + kb * 64, f);
-            else neg = finish_group<true>(v0, bias + kb * 64, f);
+            if (l == 8) finish_group<false>(v0, bias + kb * 64, f);
+            else finish_group<true>(v0, bias + kb * 64, f);
             if (l == 7) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) sigma_part = fmaf(f[i], sC[kCW8Row0 + kb * 64 + i], sigma_part);
             }
-            if (kTrain && l < 8) mask_tile[(l * 8 + 2 * kb) * kTileM + row] = neg;
+            if (kTrain && l < 8) mask_tile[(l * 8 + 2 * kb) * kTileM + row] = relu_mask(f);
             store_group(f, blk_row, row, 0);
-            if (l == 8) neg = finish_group<false>(v1, bias + kb * 64 + 32, f);
-            else neg = finish_group<true>(v1, bias + kb * 64 + 32, f);
+            if (l == 8) finish_group<false>(v1, bias + kb * 64 + 32, f);
+            else finish_group<true>(v1, bias + kb * 64 + 32, f);
             if (l == 7) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) sigma_part = fmaf(f[i], sC[kCW8Row0 + kb * 64 + 32 + i], sigma_part);
             }
-            if (kTrain && l < 8) mask_tile[(l * 8 + 2 * kb + 1) * kTileM + row] = neg;
+            if (kTrain && l < 8) mask_tile[(l * 8 + 2 * kb + 1) * kTileM + row] = relu_mask(f);
             store_group(f, blk_row, row, 4);
             fence_proxy_async();
             if (kTrain) {
@@ -347,11 +359,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
           if (l == 7 && half == 1) sX[row * 4 + 3] = sigma_part;
           if (stamp) a.prof[((tile_iter * kNumFwdLayers + l) * 8) + 3] = clock64();
         } else {
-          // fc_9 output (128 columns = one N-half): this warp group owns columns [64*half, 64*half + 64)
-          mbar_wait(&acc_full[2], accn[2] & 1);
-          ++accn[2];
-          tc_fence_after();
-          if (stamp) a.prof[((tile_iter * kNumFwdLayers + l) * 8) + 2] = clock64();
+          // fc_9 output (128 columns): this half owns columns [64*half, 64*half + 64)
           uint32_t v0[32], v1[32];
           tmem_ld32(taddr + half * 64, v0);
           tmem_ld32(taddr + half * 64 + 32, v1);
@@ -361,7 +369,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
           }
           tmem_ld_wait();
           float f[32];
-          uint32_t neg = finish_group<true>(v0, bias + half * 64, f);
+          finish_group<true>(v0, bias + half * 64, f);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             rgb0 = fmaf(f[i], sC[kCWout + half * 64 + i], rgb0);
@@ -369,10 +377,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
             rgb2 = fmaf(f[i], sC[kCWout + 256 + half * 64 + i], rgb2);
           }
           if (kTrain) {
-            mask_tile[(64 + 2 * half) * kTileM + row] = neg;
+            mask_tile[(64 + 2 * half) * kTileM + row] = relu_mask(f);
             store_group(f, a_row + half * kBlockBytes, row, 0);
           }
-          neg = finish_group<true>(v1, bias + half * 64 + 32, f);
+          finish_group<true>(v1, bias + half * 64 + 32, f);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             rgb0 = fmaf(f[i], sC[kCWout + half * 64 + 32 + i], rgb0);
@@ -380,7 +388,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
             rgb2 = fmaf(f[i], sC[kCWout + 256 + half * 64 + 32 + i], rgb2);
           }
           if (kTrain) {
-            mask_tile[(64 + 2 * half + 1) * kTileM + row] = neg;
+            mask_tile[(64 + 2 * half + 1) * kTileM + row] = relu_mask(f);
             store_group(f, a_row + half * kBlockBytes, row, 4);
             fence_proxy_async();
             __syncwarp();
