@@ -127,3 +127,14 @@ def test_bf16_backward_vs_bf16_emulating_oracle(tn, m):
     # isolated entries differ by a few % where a bf16 rounding tie or a ReLU mask bit falls the other way
     bad = [r for r in report if r[1] > 1e-1 or r[2] < 0.9995]
     assert not bad, "\n".join(f"{k}: relmax {e:.4f} cos {c:.6f}" for k, e, c in report)
+
+
+@pytest.mark.parametrize("n,k", [(128, 256), (256, 128), (128, 64)])
+def test_umma_a_from_tmem(tn, n, k):
+    """TS form: A operand written to TMEM with tcgen05.st as packed bf16 pairs (the chain kernels' operand path)."""
+    torch.manual_seed(n * 7 + k)
+    a = torch.randn(128, k, device="cuda").bfloat16()
+    b = torch.randn(n, k, device="cuda").bfloat16()
+    d = _umma(tn, a.view(torch.int16), b.view(torch.int16), n, k, 2)
+    ref = a.float() @ b.float().t()
+    torch.testing.assert_close(d, ref, rtol=1e-4, atol=1e-3)

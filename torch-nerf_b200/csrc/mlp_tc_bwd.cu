@@ -27,12 +27,14 @@ using namespace tc;
 // ================================================================================================
 // 1. dgrad chain
 // ================================================================================================
-constexpr int kDgStages = 4;
-constexpr int kDgStageBytes = 32768;
+constexpr int kDgStages = 9;
+constexpr int kDgStageBytes = kChunkBytes;  // 128 input features x 64 output features
 constexpr int kDgThreads = 320;
 constexpr int kDgEpiThreads = 256;
-constexpr int kDgSmA = 0;
+constexpr int kDgSmA = 0;      // staging of the bf16 gradient blocks for the bulk stores (the MMA A operand lives in TMEM)
 constexpr int kDgSmW = 65536;
+// tensor memory map (columns): fp32 accumulator [0,256) (two N-halves), A operand buffers [256,384) and [384,512)
+constexpr uint32_t kDgTmA = 256;
 constexpr int kDgSmC = kDgSmW + kDgStages * kDgStageBytes;  // w8row0 (256) | wout (384)
 constexpr int kDgSmBar = kDgSmC + 640 * 4;
 constexpr int kDgSmTotal = kDgSmBar + 256;
@@ -48,23 +50,28 @@ struct DgradArgs {
   int64_t m;
 };
 
-__device__ __forceinline__ void masked_group(const uint32_t (&v)[32], uint32_t mask, float add_scale,
+// `neg` holds the sign bits of the forward pre-activations, column i at bit (31 - i): set = ReLU was inactive
+__device__ __forceinline__ void masked_group(const uint32_t (&v)[32], uint32_t neg, float add_scale,
                                              const float* __restrict__ add_vec, float (&f)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
     float t = __uint_as_float(v[i]);
     if (add_vec != nullptr) t = fmaf(add_scale, add_vec[i], t);
-    f[i] = ((mask >> i) & 1u) ? t : 0.f;
+    f[i] = ((neg >> (31 - i)) & 1u) ? 0.f : t;
   }
 }
 
-__device__ __forceinline__ void store_group_bf16(const float (&f)[32], uint8_t* blk_row, int row, int chunk0) {
+__device__ __forceinline__ void pack_words(const float (&f)[32], uint32_t* w) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint4 qv = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
-                          pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
-    *reinterpret_cast<uint4*>(blk_row + (((chunk0 + j) ^ (row & 7)) << 4)) = qv;
-  }
+  for (int j = 0; j < 16; ++j) w[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
+}
+
+// 16 packed words (32 columns) -> four 16-byte chunks of a swizzled tile-image row
+__device__ __forceinline__ void store_words(const uint32_t* w, uint8_t* blk_row, int row, int chunk0) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<uint4*>(blk_row + (((chunk0 + j) ^ (row & 7)) << 4)) =
+        make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
 }
 
 __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
@@ -77,7 +84,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
   uint64_t* full = bars;
   uint64_t* empty = bars + kDgStages;
   uint64_t* a_ready = bars + 2 * kDgStages;  // [4]
-  uint64_t* acc_full = a_ready + 4;          // [2]
+  uint64_t* acc_full = a_ready + 4;          // [2 N-halves of the accumulator]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -108,18 +115,14 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
     if (lane == 0) {
       uint32_t g = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint8_t* layer_src = a.packed + kPackedBwdOff;
-        for (int j = 0; j < kNumBwdLayers; ++j) {
-          const int nk = bwd_nk(j);
-          for (int i = 0; i < nk; ++i) {
-            const int kb = nk == 4 ? kb_order(i) : i;
-            const uint32_t s = g % kDgStages, ph = (g / kDgStages) & 1;
-            mbar_wait(&empty[s], ph ^ 1);
-            mbar_arrive_expect_tx(&full[s], kDgStageBytes);
-            bulk_g2s(sW + s * kDgStageBytes, layer_src + (size_t)kb * kDgStageBytes, kDgStageBytes, &full[s]);
-            ++g;
-          }
-          layer_src += (size_t)nk * kDgStageBytes;
+        const uint8_t* src = a.packed + kPackedBwdOff;
+        for (int c = 0; c < kBwdChunks; ++c) {
+          const uint32_t s = g % kDgStages, ph = (g / kDgStages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], kDgStageBytes);
+          bulk_g2s(sW + s * kDgStageBytes, src, kDgStageBytes, &full[s]);
+          src += kDgStageBytes;
+          ++g;
         }
       }
     }
@@ -127,38 +130,38 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
     if (lane == 0) {
       uint32_t g = 0;
       uint32_t a_cnt[4] = {0, 0, 0, 0};
-      constexpr uint32_t idesc = make_idesc_bf16(256, false, false);
-      const uint32_t sA_u = smem_u32(sA), sW_u = smem_u32(sW);
+      constexpr uint32_t idesc = make_idesc_bf16(128, false, false);
+      const uint32_t sW_u = smem_u32(sW);
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int j = 0; j < kNumBwdLayers; ++j) {
-          const uint32_t acc = tmem_base + (uint32_t)(j & 1) * 256u;
           const int nk = bwd_nk(j);
-          if (j == 0) {
-            // both column halves must have left the previous tile's last epilogue (they read accumulator 0, which
-            // this layer overwrites) -- each half signals its G9 block only after that
-            mbar_wait(&a_ready[0], a_cnt[0] & 1);
-            mbar_wait(&a_ready[1], a_cnt[1] & 1);
-            ++a_cnt[0];
-            ++a_cnt[1];
-          }
+          const uint32_t a_tm = tmem_base + kDgTmA + (uint32_t)(j & 1) * 128u;  // this layer's A operand (G) in TMEM
+          // N-half 0 overwrites accumulator columns [0,128): both warp groups must have drained them, which each
+          // signals through its first gradient block (for j == 0: the G9 blocks, written after the previous tile)
+          mbar_wait(&a_ready[0], a_cnt[0] & 1);
+          mbar_wait(&a_ready[1], a_cnt[1] & 1);
+          ++a_cnt[0];
+          ++a_cnt[1];
+          for (int nh = 0; nh < 2; ++nh) {
+            const uint32_t acc = tmem_base + (uint32_t)nh * 128u;
 #pragma unroll 1
-          for (int i = 0; i < nk; ++i) {
-            const int kb = nk == 4 ? kb_order(i) : i;
-            if (j > 0) {
-              mbar_wait(&a_ready[kb], a_cnt[kb] & 1);
-              ++a_cnt[kb];
-            }
-            const uint32_t s = g % kDgStages, ph = (g / kDgStages) & 1;
-            mbar_wait(&full[s], ph);
-            tc_fence_after();
-            const uint64_t da = desc_kmajor(sA_u + kb * kBlockBytes);
-            const uint64_t db = desc_kmajor(sW_u + s * kDgStageBytes);
+            for (int kb = 0; kb < nk; ++kb) {
+              if (nh == 0 && kb >= 2) {
+                mbar_wait(&a_ready[kb], a_cnt[kb] & 1);
+                ++a_cnt[kb];
+              }
+              const uint32_t s = g % kDgStages, ph = (g / kDgStages) & 1;
+              mbar_wait(&full[s], ph);
+              tc_fence_after();
+              const uint64_t db = desc_kmajor(sW_u + s * kDgStageBytes);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
-            umma_commit(&empty[s]);
-            ++g;
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_ts(acc, a_tm + (uint32_t)(kb * 32 + k * 8), db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              umma_commit(&empty[s]);
+              ++g;
+            }
+            umma_commit(&acc_full[nh]);
           }
-          umma_commit(&acc_full[j & 1]);
         }
       }
     }
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
     const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t accn0 = 0, accn1 = 0;
+    uint32_t accn[2] = {0, 0};
     uint8_t* a_row = sA + row * 128;
     float4* ghead_out = reinterpret_cast<float4*>(a.scratch + scratch_ghead_offset(a.m));
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -190,6 +193,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
       {
         if (lane == 0) bulk_wait_read<1>();
         __syncwarp();
+        uint32_t w[32];
 #pragma unroll
         for (int gi = 0; gi < 2; ++gi) {
           const int col0 = half * 64 + gi * 32;
@@ -200,36 +204,37 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
             float t = gz0 * sWout[col0 + i];
             t = fmaf(gz1, sWout[128 + col0 + i], t);
             t = fmaf(gz2, sWout[256 + col0 + i], t);
-            f[i] = ((mk >> i) & 1u) ? t : 0.f;
+            f[i] = ((mk >> (31 - i)) & 1u) ? 0.f : t;
           }
-          store_group_bf16(f, a_row + half * kBlockBytes, row, gi * 4);
+          pack_words(f, w + 16 * gi);
         }
+        tmem_st32(lane_addr + kDgTmA + half * 32, w);  // layer 0 reads A buffer 0
+        store_words(w, a_row + half * kBlockBytes, row, 0);
+        store_words(w + 16, a_row + half * kBlockBytes, row, 4);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
           bulk_s2g(g_tile + (size_t)(kGradG9 + half) * kBlockBytes + q * 4096, sA + half * kBlockBytes + q * 4096, 4096);
           bulk_commit();
         }
+        tmem_st_wait();
+        tc_fence_before();
         mbar_arrive(&a_ready[half]);
       }
       for (int j = 0; j < kNumBwdLayers; ++j) {
-        if (j & 1) {
-          mbar_wait(&acc_full[1], accn1 & 1);
-          ++accn1;
-        } else {
-          mbar_wait(&acc_full[0], accn0 & 1);
-          ++accn0;
-        }
-        tc_fence_after();
-        const uint32_t taddr = lane_addr + (uint32_t)(j & 1) * 256u;
+        const uint32_t taddr = lane_addr;
+        const uint32_t a_next = lane_addr + kDgTmA + (uint32_t)((j + 1) & 1) * 128u;
         const int slot = 8 - j;  // ReLU mask of the layer output this gradient flows into (j >= 1): h7 .. h0
 #pragma unroll 1
         for (int t = 0; t < 2; ++t) {
-          const int kb = half + 2 * t;
+          const int kb = half + 2 * t;  // N-half t, this warp group's 64 columns of it
+          mbar_wait(&acc_full[t], accn[t] & 1);
+          ++accn[t];
+          tc_fence_after();
           uint32_t v0[32], v1[32];
           tmem_ld32(taddr + kb * 64, v0);
           tmem_ld32(taddr + kb * 64 + 32, v1);
-          uint32_t m0 = 0xffffffffu, m1 = 0xffffffffu;
+          uint32_t m0 = 0u, m1 = 0u;  // sign-bit masks: 0 = every column passes (layer j = 0 has no ReLU)
           if (j >= 1) {
             m0 = __ldg(mask_tile + (slot * 8 + 2 * kb) * kTileM + row);
             m1 = __ldg(mask_tile + (slot * 8 + 2 * kb + 1) * kTileM + row);
@@ -244,18 +249,27 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
           tmem_ld_wait();
           uint8_t* blk_row = a_row + kb * kBlockBytes;
           float f[32];
+          uint32_t w[32];
           masked_group(v0, m0, gsp, j == 1 ? sW8 + kb * 64 : nullptr, f);
-          store_group_bf16(f, blk_row, row, 0);
+          pack_words(f, w);
           masked_group(v1, m1, gsp, j == 1 ? sW8 + kb * 64 + 32 : nullptr, f);
-          store_group_bf16(f, blk_row, row, 4);
+          pack_words(f, w + 16);
+          if (j < kNumBwdLayers - 1) tmem_st32(a_next + kb * 32, w);
+          store_words(w, blk_row, row, 0);
+          store_words(w + 16, blk_row, row, 4);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
             bulk_s2g(g_tile + (size_t)(2 + 4 * j + kb) * kBlockBytes + q * 4096, sA + kb * kBlockBytes + q * 4096, 4096);
             bulk_commit();
           }
-          tc_fence_before();
-          if (j < kNumBwdLayers - 1) mbar_arrive(&a_ready[kb]);
+          if (j < kNumBwdLayers - 1) {
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&a_ready[kb]);
+          } else {
+            tc_fence_before();
+          }
         }
       }
     }

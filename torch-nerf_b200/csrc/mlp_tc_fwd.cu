@@ -1,18 +1,27 @@
 // K4+K5 on the sm_100a tensor cores: the NeRF MLP forward (network/nerf.py:65-121) as a chain of tcgen05 BF16 MMAs
 // with fp32 accumulation in TMEM; positional encoding (signal_encoder/positional_encoder.py:49-104, as applied by
 // scene/primitives/cube.py:62-69) is computed in-kernel as the first layer's operand; weights are streamed from L2
-// by the TMA engine (cp.async.bulk + mbarrier) through a 3-stage ring.
+// by the TMA engine (cp.async.bulk + mbarrier) through a 7-stage ring of 16 KB chunks (128 outputs x 64 inputs).
 //
-// One CTA per SM, 128 sample rows per tile, activations never leave the SM (inference).  In training mode the
-// kernel additionally writes every layer input as a tile image plus ReLU bit masks into the training cache.
+// One CTA per SM, 128 sample rows per tile.  Activations live in TENSOR MEMORY between layers:
 //
-//   warp 0      weight loader   1-D bulk copies of pre-swizzled bf16 weight chunks (N x 64)
-//   warp 1      MMA issuer      one thread issues tcgen05.mma (M=128, N=256|128, K=16); accumulators ping-pong
-//                               between TMEM columns [0,256) and [256,512) from layer to layer
-//   warps 2-9   epilogue        two warps per TMEM lane quarter (column halves): tcgen05.ld -> +bias, ReLU -> bf16
-//                               -> swizzled smem = next layer's A operand, signalled per 64-column k-block so the
-//                               next layer's MMAs start while the rest of the accumulator is still being drained;
-//                               the same warps build the encoded inputs of the next tile
+//   TMEM columns [0,256)    fp32 accumulator of the current layer (two N-halves of 128 columns)
+//                [256,384)  A operand buffer 0  (128 rows x 256 bf16 as packed pairs)   \ ping-pong: layer l reads
+//                [384,512)  A operand buffer 1                                          / buffer l&1, writes (l+1)&1
+//
+//   warp 0      weight loader   1-D bulk copies of pre-swizzled bf16 weight chunks
+//   warp 1      MMA issuer      one thread issues tcgen05.mma (M=128, N=128, K=16) in the TS form: A from TMEM, B from
+//                               shared memory -- this takes the activations off the shared-memory port, which limits
+//                               the SS form to one 128x256x16 MMA per 168 cycles.  A 256-wide layer is two N-halves
+//                               committed separately: while the tensor pipe computes output columns [128,256) the
+//                               epilogue already drains [0,128), and the next layer's first MMAs (which only need the
+//                               k-blocks produced from half 0) start the moment half 1 is issued.
+//   warps 2-9   epilogue        two warps per TMEM lane quarter: tcgen05.ld -> +bias, ReLU -> bf16 pairs -> tcgen05.st
+//                               into the other A buffer, signalled per 64-column k-block; the same warps build the
+//                               encoded inputs of the next tile (those two k-blocks stay in shared memory, SS form)
+//
+// In training mode the epilogue additionally writes every layer input as a tile image (through a shared-memory staging
+// area and per-warp 4 KB bulk stores) plus ReLU sign-bit masks into the training cache.
 //
 // Tensor-core layers: fc_in, fc_1..fc_7, fc_8 rows 1..256 (features), fc_9.  The density head (fc_8 row 0,
 // nerf.py:115) and fc_out + sigmoid (nerf.py:119) are fp32 dot products in the epilogues of layers 7 and 9,
@@ -27,26 +36,22 @@
 namespace nerf {
 using namespace tc;
 
-// i-th weight chunk (= k-block of the layer's K dimension) consumed by layer l.  4-block layers follow kb_order;
-// the 5-block layers put the block that does not depend on the previous epilogue first (fc_5: encoded position,
-// chunk 0) or keep it last (fc_9: encoded view direction, chunk 4).
-__host__ __device__ constexpr int fwd_chunk(int l, int i) {
-  return fwd_nk(l) == 4 ? kb_order(i) : (l == 5 ? (i == 0 ? 0 : 1 + kb_order(i - 1)) : (l == 9 ? (i < 4 ? kb_order(i) : 4) : i));
-}
-
-constexpr int kStages = 3;
-constexpr int kStageBytes = 32768;
+constexpr int kStages = 7;
+constexpr int kStageBytes = kChunkBytes;  // 128 output rows x 64 K-columns
 constexpr int kFwdThreads = 320;
 constexpr int kEpiThreads = 256;
 // shared memory map (bytes from the 1024-aligned base)
-constexpr int kSmA = 0;                         // 4 k-blocks x 16 KB : current activations (A operand)
-constexpr int kSmIn = 65536;                    // pe block 16 KB | de block 16 KB
+constexpr int kSmStage = 0;                     // 4 blocks x 16 KB: staging of bf16 activations for the cache (training)
+constexpr int kSmIn = 65536;                    // pe block 16 KB | de block 16 KB (A operands of the SS-form chunks)
 constexpr int kSmW = 98304;                     // weight ring
 constexpr int kSmC = kSmW + kStages * kStageBytes;
-constexpr int kSmX = kSmC + kCFloats * 4;       // 128 x 4 floats: partial sigma / rgb exchange between column halves
+constexpr int kSmX = kSmC + kCFloats * 4;       // 128 x 4 floats: partial sigma / rgb exchange between warp groups
 constexpr int kSmBar = kSmX + 128 * 16;
 constexpr int kSmTotal = kSmBar + 256;
 constexpr int kFwdSmemBytes = kSmTotal + 1024;  // + alignment slack
+// tensor memory map (columns)
+constexpr uint32_t kTmAcc = 0;
+constexpr uint32_t kTmA = 256;                  // two A buffers of 128 columns
 
 struct FwdArgs {
   const uint8_t* packed;
@@ -96,42 +101,48 @@ __device__ __forceinline__ void encode_row(float x, float y, float z, uint8_t* r
   }
 }
 
-// 32 accumulator columns -> +bias -> (ReLU) -> bf16 -> four 16-byte chunks of the A operand row
+// 32 accumulator columns -> +bias -> (ReLU).  Returns the sign bits of the pre-activations, element i at bit
+// (31 - i): one funnel shift per element (the training cache's ReLU mask, see mlp_tc_layout.cuh).
 template <bool RELU>
-__device__ __forceinline__ void finish_group(const uint32_t (&v)[32], const float* __restrict__ bias, float (&f)[32]) {
+__device__ __forceinline__ uint32_t finish_group(const uint32_t (&v)[32], const float* __restrict__ bias, float (&f)[32]) {
+  uint32_t neg = 0;
 #pragma unroll
   for (int i = 0; i < 32; i += 4) {
     const float4 b = *reinterpret_cast<const float4*>(bias + i);
-    float t0 = __uint_as_float(v[i]) + b.x, t1 = __uint_as_float(v[i + 1]) + b.y;
-    float t2 = __uint_as_float(v[i + 2]) + b.z, t3 = __uint_as_float(v[i + 3]) + b.w;
-    if (RELU) {
-      t0 = fmaxf(t0, 0.f), t1 = fmaxf(t1, 0.f), t2 = fmaxf(t2, 0.f), t3 = fmaxf(t3, 0.f);
+    const float t[4] = {__uint_as_float(v[i]) + b.x, __uint_as_float(v[i + 1]) + b.y, __uint_as_float(v[i + 2]) + b.z,
+                        __uint_as_float(v[i + 3]) + b.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (RELU) {
+        neg = __funnelshift_l(__float_as_uint(t[e]), neg, 1);
+        f[i + e] = fmaxf(t[e], 0.f);
+      } else {
+        f[i + e] = t[e];
+      }
     }
-    f[i] = t0, f[i + 1] = t1, f[i + 2] = t2, f[i + 3] = t3;
   }
+  return neg;
 }
 
-__device__ __forceinline__ uint32_t relu_mask(const float (&f)[32]) {
-  uint32_t m = 0;
+// 32 fp32 values -> 16 packed bf16 pairs
+__device__ __forceinline__ void pack_group(const float (&f)[32], uint32_t* w) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) m |= (f[i] > 0.f ? 1u : 0u) << i;
-  return m;
+  for (int j = 0; j < 16; ++j) w[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
 }
 
-__device__ __forceinline__ void store_group(const float (&f)[32], uint8_t* blk_row, int row, int chunk0) {
+// 16 packed words (32 columns) -> four 16-byte chunks of a swizzled tile-image row
+__device__ __forceinline__ void store_words(const uint32_t* w, uint8_t* blk_row, int row, int chunk0) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint4 qv = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
-                          pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
-    *reinterpret_cast<uint4*>(blk_row + (((chunk0 + j) ^ (row & 7)) << 4)) = qv;
-  }
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<uint4*>(blk_row + (((chunk0 + j) ^ (row & 7)) << 4)) =
+        make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
 }
 
 template <bool kTrain>
 __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sA = smem + kSmA;
+  uint8_t* sStage = smem + kSmStage;
   uint8_t* sIn = smem + kSmIn;
   uint8_t* sW = smem + kSmW;
   float* sC = reinterpret_cast<float*>(smem + kSmC);
@@ -141,7 +152,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
   uint64_t* empty = bars + kStages;        // [kStages]
   uint64_t* a_ready = bars + 2 * kStages;  // [4]   one completion per producing layer
   uint64_t* in_ready = a_ready + 4;        // [1]   one completion per tile
-  uint64_t* acc_full = in_ready + 1;       // [2]
+  uint64_t* acc_full = in_ready + 1;       // [2 N-halves of the accumulator]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -173,19 +184,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
     if (lane == 0) {
       uint32_t g = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint8_t* layer_src = a.packed + kPackedFwdOff;
-        for (int l = 0; l < kNumFwdLayers; ++l) {
-          const uint32_t bytes = fwd_n(l) * 128;
-          const int nk = fwd_nk(l);
-          for (int i = 0; i < nk; ++i) {
-            const int kb = fwd_chunk(l, i);
-            const uint32_t s = g % kStages, ph = (g / kStages) & 1;
-            mbar_wait(&empty[s], ph ^ 1);
-            mbar_arrive_expect_tx(&full[s], bytes);
-            bulk_g2s(sW + s * kStageBytes, layer_src + (size_t)kb * bytes, bytes, &full[s]);
-            ++g;
-          }
-          layer_src += (size_t)nk * bytes;
+        const uint8_t* src = a.packed + kPackedFwdOff;
+        for (int c = 0; c < kFwdChunks; ++c) {
+          const uint32_t s = g % kStages, ph = (g / kStages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], kStageBytes);
+          bulk_g2s(sW + s * kStageBytes, src, kStageBytes, &full[s]);
+          src += kStageBytes;
+          ++g;
         }
       }
     }
@@ -193,49 +199,66 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       uint32_t g = 0, a_cnt = 0, in_cnt = 0;
-      constexpr uint32_t idesc256 = make_idesc_bf16(256, false, false);
-      constexpr uint32_t idesc128 = make_idesc_bf16(128, false, false);
-      const uint32_t sA_u = smem_u32(sA), sIn_u = smem_u32(sIn), sW_u = smem_u32(sW);
+      constexpr uint32_t idesc = make_idesc_bf16(128, false, false);
+      const uint32_t sIn_u = smem_u32(sIn), sW_u = smem_u32(sW);
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // the encoded inputs are ready; all epilogue warps have also left the previous tile (accumulator drained)
         mbar_wait(in_ready, in_cnt & 1);
         ++in_cnt;
         for (int l = 0; l < kNumFwdLayers; ++l) {
-          const uint32_t acc = tmem_base + (uint32_t)(l & 1) * 256u;
-          const uint32_t idesc = (l == 9) ? idesc128 : idesc256;
           const int nk = fwd_nk(l);
+          const uint32_t a_tm = tmem_base + kTmA + (uint32_t)(l & 1) * 128u;  // this layer's A operand in TMEM
           const bool stamp = a.prof != nullptr && blockIdx.x == 0 && (int)in_cnt <= a.prof_tiles;
           if (stamp) a.prof[(((int)in_cnt - 1) * kNumFwdLayers + l) * 8 + 0] = clock64();
           long long wait_a = 0, wait_w = 0;
-          for (int i = 0; i < nk; ++i) {
-            const int kb = fwd_chunk(l, i);
-            uint32_t a_addr;
-            int nsteps = 4;
-            if (l == 0 || (l == 5 && kb == 0)) {
-              a_addr = sIn_u;                      // encoded position
-            } else if (l == 9 && kb == 4) {
-              a_addr = sIn_u + kBlockBytes;        // encoded view direction (K = 32)
-              nsteps = 2;
-            } else {
-              const int ab = (l == 5) ? kb - 1 : kb;
-              // a_ready[ab] completes once per producing layer 0..8; layer l consumes round (l - 1)
-              const long long w0 = stamp ? clock64() : 0;
-              mbar_wait(&a_ready[ab], (a_cnt + (uint32_t)(l - 1)) & 1);
-              if (stamp) wait_a += clock64() - w0;
-              a_addr = sA_u + ab * kBlockBytes;
-            }
-            const uint32_t s = g % kStages, ph = (g / kStages) & 1;
-            const long long w1 = stamp ? clock64() : 0;
-            mbar_wait(&full[s], ph);
-            if (stamp) wait_w += clock64() - w1;
-            tc_fence_after();
-            const uint64_t da = desc_kmajor(a_addr);
-            const uint64_t db = desc_kmajor(sW_u + s * kStageBytes);
-#pragma unroll 4
-            for (int k = 0; k < nsteps; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
-            umma_commit(&empty[s]);
-            ++g;
+          // a_ready[b] completes once per producing layer 0..8; layer l >= 1 consumes round (l - 1)
+          const uint32_t a_par = (a_cnt + (uint32_t)(l - 1)) & 1;
+          if (l >= 1) {
+            // N-half 0 overwrites accumulator columns [0,128): both warp groups must have drained them
+            const long long w0 = stamp ? clock64() : 0;
+            mbar_wait(&a_ready[0], a_par);
+            mbar_wait(&a_ready[1], a_par);
+            if (stamp) wait_a += clock64() - w0;
           }
-          umma_commit(&acc_full[l & 1]);
+          for (int nh = 0; nh < fwd_nh(l); ++nh) {
+            const uint32_t acc = tmem_base + kTmAcc + (uint32_t)nh * 128u;
+            for (int kb = 0; kb < nk; ++kb) {
+              int ab = -1;             // A k-block in TMEM, or -1 for the shared-memory blocks
+              uint32_t a_smem = 0;
+              int nsteps = 4;
+              if (l == 0 || (l == 5 && kb == 0)) {
+                a_smem = sIn_u;                      // encoded position
+              } else if (l == 9 && kb == 4) {
+                a_smem = sIn_u + kBlockBytes;        // encoded view direction (K = 32)
+                nsteps = 2;
+              } else {
+                ab = (l == 5) ? kb - 1 : kb;
+                if (nh == 0 && ab >= 2) {
+                  const long long w0 = stamp ? clock64() : 0;
+                  mbar_wait(&a_ready[ab], a_par);
+                  if (stamp) wait_a += clock64() - w0;
+                }
+              }
+              const uint32_t s = g % kStages, ph = (g / kStages) & 1;
+              const long long w1 = stamp ? clock64() : 0;
+              mbar_wait(&full[s], ph);
+              if (stamp) wait_w += clock64() - w1;
+              tc_fence_after();
+              const uint64_t db = desc_kmajor(sW_u + s * kStageBytes);
+              if (ab >= 0) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16_ts(acc, a_tm + (uint32_t)(ab * 32 + k * 8), db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              } else {
+                const uint64_t da = desc_kmajor(a_smem);
+#pragma unroll 4
+                for (int k = 0; k < nsteps; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              }
+              umma_commit(&empty[s]);
+              ++g;
+            }
+            umma_commit(&acc_full[nh]);
+          }
           if (stamp) {
             unsigned long long* pr = a.prof + (((int)in_cnt - 1) * kNumFwdLayers + l) * 8;
             pr[1] = clock64();
@@ -249,11 +272,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
   } else {
     // ------------------------------------------------------------------ epilogue warps
     const int q = warp & 3;             // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;   // column half: k-blocks {half, half + 2}
+    const int half = (warp - 2) >> 2;   // warp group: drains k-block `half` of N-half 0 and k-block `2 + half` of N-half 1
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t accn0 = 0, accn1 = 0;
-    uint8_t* a_row = sA + row * 128;
+    uint32_t accn[2] = {0, 0};  // completions seen per N-half barrier
+    uint8_t* st_row = sStage + row * 128;
     int tile_iter = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_iter) {
       const int64_t grow = tile * kTileM + row;
@@ -303,63 +326,70 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
       float sigma_part = 0.f;
       float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
       for (int l = 0; l < kNumFwdLayers; ++l) {
-        if (l & 1) {
-          mbar_wait(&acc_full[1], accn1 & 1);
-          ++accn1;
-        } else {
-          mbar_wait(&acc_full[0], accn0 & 1);
-          ++accn0;
-        }
-        tc_fence_after();
-        if (stamp) a.prof[((tile_iter * kNumFwdLayers + l) * 8) + 2] = clock64();
-        const uint32_t taddr = lane_addr + (uint32_t)(l & 1) * 256u;
+        const uint32_t taddr = lane_addr + kTmAcc;
+        const uint32_t a_next = lane_addr + kTmA + (uint32_t)((l + 1) & 1) * 128u;  // next layer's A operand
         const float* bias = sC + ((l < 8) ? kCBias + 256 * l : (l == 8 ? kCBias8 : kCBias9));
         if (l < 9) {
 #pragma unroll 1
           for (int t = 0; t < 2; ++t) {
+            // N-half t of the layer is complete: this warp drains its 64 columns of it = k-block kb of the next layer
             const int kb = half + 2 * t;
+            mbar_wait(&acc_full[t], accn[t] & 1);
+            ++accn[t];
+            tc_fence_after();
+            if (stamp && t == 0) a.prof[((tile_iter * kNumFwdLayers + l) * 8) + 2] = clock64();
             uint32_t v0[32], v1[32];
             tmem_ld32(taddr + kb * 64, v0);
             tmem_ld32(taddr + kb * 64 + 32, v1);
             if (kTrain) {
-              if (lane == 0) bulk_wait_read<1>();  // this warp's previous store out of block kb has been read
+              if (lane == 0) bulk_wait_read<1>();  // this warp's previous store out of staging block kb has been read
               __syncwarp();
             }
             tmem_ld_wait();
-            uint8_t* blk_row = a_row + kb * kBlockBytes;
             float f[32];
-            if (l == 8) finish_group<false>(v0, bias + kb * 64, f);
-            else finish_group<true>(v0, bias + kb * 64, f);
+            uint32_t w[32];
+            uint32_t neg;
+            if (l == 8) neg = finish_group<false>(v0, bias + kb * 64, f);
+            else neg = finish_group<true>(v0, bias + kb * 64, f);
             if (l == 7) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) sigma_part = fmaf(f[i], sC[kCW8Row0 + kb * 64 + i], sigma_part);
             }
-            if (kTrain && l < 8) mask_tile[(l * 8 + 2 * kb) * kTileM + row] = relu_mask(f);
-            store_group(f, blk_row, row, 0);
-            if (l == 8) finish_group<false>(v1, bias + kb * 64 + 32, f);
-            else finish_group<true>(v1, bias + kb * 64 + 32, f);
+            if (kTrain && l < 8) mask_tile[(l * 8 + 2 * kb) * kTileM + row] = neg;
+            pack_group(f, w);
+            if (l == 8) neg = finish_group<false>(v1, bias + kb * 64 + 32, f);
+            else neg = finish_group<true>(v1, bias + kb * 64 + 32, f);
             if (l == 7) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) sigma_part = fmaf(f[i], sC[kCW8Row0 + kb * 64 + 32 + i], sigma_part);
             }
-            if (kTrain && l < 8) mask_tile[(l * 8 + 2 * kb + 1) * kTileM + row] = relu_mask(f);
-            store_group(f, blk_row, row, 4);
-            fence_proxy_async();
+            if (kTrain && l < 8) mask_tile[(l * 8 + 2 * kb + 1) * kTileM + row] = neg;
+            pack_group(f, w + 16);
+            tmem_st32(a_next + kb * 32, w);  // 64 bf16 = 32 packed columns of this row
             if (kTrain) {
+              uint8_t* blk_row = st_row + kb * kBlockBytes;
+              store_words(w, blk_row, row, 0);
+              store_words(w + 16, blk_row, row, 4);
+              fence_proxy_async();
               __syncwarp();
               if (lane == 0) {
                 const int blk = (l < 8 ? cache_h(l) : kCacheFeat) + kb;
-                bulk_s2g(cache_tile + (size_t)blk * kBlockBytes + q * 4096, sA + kb * kBlockBytes + q * 4096, 4096);
+                bulk_s2g(cache_tile + (size_t)blk * kBlockBytes + q * 4096, sStage + kb * kBlockBytes + q * 4096, 4096);
                 bulk_commit();
               }
             }
+            tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&a_ready[kb]);
           }
           if (l == 7 && half == 1) sX[row * 4 + 3] = sigma_part;
           if (stamp) a.prof[((tile_iter * kNumFwdLayers + l) * 8) + 3] = clock64();
         } else {
-          // fc_9 output (128 columns): this half owns columns [64*half, 64*half + 64)
+          // fc_9 output (128 columns = one N-half): this warp group owns columns [64*half, 64*half + 64)
+          mbar_wait(&acc_full[0], accn[0] & 1);
+          ++accn[0];
+          tc_fence_after();
+          if (stamp) a.prof[((tile_iter * kNumFwdLayers + l) * 8) + 2] = clock64();
           uint32_t v0[32], v1[32];
           tmem_ld32(taddr + half * 64, v0);
           tmem_ld32(taddr + half * 64 + 32, v1);
@@ -369,7 +399,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
           }
           tmem_ld_wait();
           float f[32];
-          finish_group<true>(v0, bias + half * 64, f);
+          uint32_t w[32];
+          uint32_t neg = finish_group<true>(v0, bias + half * 64, f);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             rgb0 = fmaf(f[i], sC[kCWout + half * 64 + i], rgb0);
@@ -377,10 +408,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
             rgb2 = fmaf(f[i], sC[kCWout + 256 + half * 64 + i], rgb2);
           }
           if (kTrain) {
-            mask_tile[(64 + 2 * half) * kTileM + row] = relu_mask(f);
-            store_group(f, a_row + half * kBlockBytes, row, 0);
+            mask_tile[(64 + 2 * half) * kTileM + row] = neg;
+            pack_group(f, w);
           }
-          finish_group<true>(v1, bias + half * 64 + 32, f);
+          neg = finish_group<true>(v1, bias + half * 64 + 32, f);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             rgb0 = fmaf(f[i], sC[kCWout + half * 64 + 32 + i], rgb0);
@@ -388,13 +419,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
             rgb2 = fmaf(f[i], sC[kCWout + 256 + half * 64 + 32 + i], rgb2);
           }
           if (kTrain) {
-            mask_tile[(64 + 2 * half + 1) * kTileM + row] = relu_mask(f);
-            store_group(f, a_row + half * kBlockBytes, row, 4);
+            mask_tile[(64 + 2 * half + 1) * kTileM + row] = neg;
+            pack_group(f, w + 16);
+            uint8_t* blk_row = st_row + half * kBlockBytes;
+            store_words(w, blk_row, row, 0);
+            store_words(w + 16, blk_row, row, 4);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-              bulk_s2g(cache_tile + (size_t)(kCacheH9 + half) * kBlockBytes + q * 4096, sA + half * kBlockBytes + q * 4096,
-                       4096);
+              bulk_s2g(cache_tile + (size_t)(kCacheH9 + half) * kBlockBytes + q * 4096,
+                       sStage + half * kBlockBytes + q * 4096, 4096);
               bulk_commit();
             }
           }

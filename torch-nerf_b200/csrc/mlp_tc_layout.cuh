@@ -18,12 +18,17 @@ constexpr int kP = 63, kV = 27, kF = 256, kH = 128;
 constexpr int kTileM = 128;
 constexpr int kBlockBytes = 16384;  // one 128 x 64 bf16 block
 
+// Weight chunks are 128 output rows x 64 K-columns (16 KB).  A 256-wide layer is computed as two N-halves: the MMAs
+// of half 0 (all K chunks) are committed on their own so the epilogue drains output columns [0,128) while the
+// tensor pipe works on half 1, and the next layer's first k-blocks are ready the moment half 1 completes.
+constexpr int kChunkBytes = 16384;
+
 // ---- forward chain: tensor-core layers fc_in, fc_1..fc_7, fc_8 (feature rows), fc_9
 constexpr int kNumFwdLayers = 10;
 __host__ __device__ constexpr int fwd_nk(int l) { return l == 0 ? 1 : ((l == 5 || l == 9) ? 5 : 4); }
-__host__ __device__ constexpr int fwd_n(int l) { return l == 9 ? kH : kF; }
-constexpr int kFwdChunks = 1 + 4 * 4 + 5 + 3 * 4 + 5;  // 39
-constexpr size_t kFwdWeightBytes = (size_t)(1 + 16 + 5 + 12) * 32768 + 5 * 16384;
+__host__ __device__ constexpr int fwd_nh(int l) { return l == 9 ? 1 : 2; }  // N-halves (fc_9 is 128 wide)
+constexpr int kFwdChunks = 2 * (1 + 4 * 4 + 5 + 3 * 4) + 5;  // 73
+constexpr size_t kFwdWeightBytes = (size_t)kFwdChunks * kChunkBytes;
 
 // Order in which the chains visit the four activation k-blocks.  The epilogue's column half h owns blocks {h, h+2}
 // and finishes h first, so blocks {0, 1} become ready before {2, 3}: natural order.  (Measured: visiting 0,2,1,3
@@ -31,11 +36,11 @@ constexpr size_t kFwdWeightBytes = (size_t)(1 + 16 + 5 + 12) * 32768 + 5 * 16384
 __host__ __device__ constexpr int kb_order(int i) { return i; }
 
 // ---- dgrad chain: layers j = 0..8 multiply by fc_9^T (128 -> 256), fc_8^T, fc_7^T, fc_6^T, fc_5^T (h4 columns),
-//      fc_4^T .. fc_1^T; every chunk is 256 rows (input features) x 64 (output features)
+//      fc_4^T .. fc_1^T; every chunk is 128 rows (input features of one N-half) x 64 (output features)
 constexpr int kNumBwdLayers = 9;
 __host__ __device__ constexpr int bwd_nk(int j) { return j == 0 ? 2 : 4; }
-constexpr int kBwdChunks = 2 + 8 * 4;  // 34
-constexpr size_t kBwdWeightBytes = (size_t)kBwdChunks * 32768;
+constexpr int kBwdChunks = 2 * (2 + 8 * 4);  // 68
+constexpr size_t kBwdWeightBytes = (size_t)kBwdChunks * kChunkBytes;
 
 // ---- fp32 constants block (float offsets)
 constexpr int kCBias = 0;        // 8 x 256 : biases of fc_in, fc_1..fc_7
@@ -61,7 +66,8 @@ constexpr int kCacheH9 = 38;                                 // fc_9 output (128
 constexpr int kCacheBlocks = 40;
 constexpr size_t kCacheTileBytes = (size_t)kCacheBlocks * kBlockBytes;
 // ReLU masks: word (slot s, 32-column group c) of row r at ((s*8 + c)*128 + r); slots 0..7 = h0..h7, slot 8 = h9
-// (4 words), word 68 bit 0 = (sigma_pre > 0)
+// (4 words).  Bit (31 - i) of a word is the SIGN BIT of the pre-activation of column 32c + i (1 = negative = no
+// gradient), collected with one funnel shift per element.  Word 68 bit 0 = (sigma_pre > 0).
 constexpr int kMaskWords = 69;
 constexpr int kMaskSigmaWord = 68;
 constexpr size_t kMaskTileBytes = (size_t)kMaskWords * kTileM * 4;

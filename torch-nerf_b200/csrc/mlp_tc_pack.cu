@@ -18,7 +18,7 @@ struct PackChunk {
   int transpose;  // 0: dst(n,k) = W[row0+n][col0+k]   1: dst(n,k) = W[row0+k][col0+n]
   uint32_t dst_off;
 };
-constexpr int kMaxPackChunks = 96;
+constexpr int kMaxPackChunks = 160;
 __constant__ PackChunk c_pack[kMaxPackChunks];
 
 __global__ void __launch_bounds__(256) pack_weights_kernel(ParamPtrs params, uint8_t* __restrict__ packed) {
@@ -67,26 +67,36 @@ static int build_pack_table(PackChunk* t) {
     t[n++] = PackChunk{param, row0, col0, ld, nrows, valid, transpose, off};
     off += (uint32_t)nrows * 128u;
   };
-  // ---- forward chain (consumption order)
-  add(W_IN, 0, 0, kP, kF, kP, 0);
+  // ---- forward chain: per layer, per N-half, per K chunk (consumption order); chunks are 128 rows
+  auto fwd_layer = [&](int param, int row0, int ld, int nh_count, auto&& cols) {
+    for (int nh = 0; nh < nh_count; ++nh) cols(param, row0 + 128 * nh, ld);
+  };
+  fwd_layer(W_IN, 0, kP, 2, [&](int p, int r, int ld) { add(p, r, 0, ld, 128, kP, 0); });
   for (int l = 1; l <= 4; ++l)
-    for (int kb = 0; kb < 4; ++kb) add(2 * l, 0, 64 * kb, kF, kF, 64, 0);       // fc_1..fc_4
-  add(W_5, 0, 0, kP + kF, kF, kP, 0);                                           // fc_5, position columns
-  for (int kb = 0; kb < 4; ++kb) add(W_5, 0, kP + 64 * kb, kP + kF, kF, 64, 0);
+    fwd_layer(2 * l, 0, kF, 2, [&](int p, int r, int ld) { for (int kb = 0; kb < 4; ++kb) add(p, r, 64 * kb, ld, 128, 64, 0); });
+  fwd_layer(W_5, 0, kP + kF, 2, [&](int p, int r, int ld) {
+    add(p, r, 0, ld, 128, kP, 0);                                                 // position columns
+    for (int kb = 0; kb < 4; ++kb) add(p, r, kP + 64 * kb, ld, 128, 64, 0);       // h4 columns
+  });
   for (int l = 6; l <= 7; ++l)
-    for (int kb = 0; kb < 4; ++kb) add(2 * l, 0, 64 * kb, kF, kF, 64, 0);       // fc_6, fc_7
-  for (int kb = 0; kb < 4; ++kb) add(W_8, 1, 64 * kb, kF, kF, 64, 0);           // fc_8 rows 1..256
-  for (int kb = 0; kb < 4; ++kb) add(W_9, 0, 64 * kb, kF + kV, kH, 64, 0);      // fc_9, feature columns
-  add(W_9, 0, kF, kF + kV, kH, kV, 0);                                          // fc_9, view columns
-  // ---- dgrad chain: dst(n = input feature, k = output feature)
+    fwd_layer(2 * l, 0, kF, 2, [&](int p, int r, int ld) { for (int kb = 0; kb < 4; ++kb) add(p, r, 64 * kb, ld, 128, 64, 0); });
+  fwd_layer(W_8, 1, kF, 2, [&](int p, int r, int ld) { for (int kb = 0; kb < 4; ++kb) add(p, r, 64 * kb, ld, 128, 64, 0); });  // rows 1..256
+  fwd_layer(W_9, 0, kF + kV, 1, [&](int p, int r, int ld) {
+    for (int kb = 0; kb < 4; ++kb) add(p, r, 64 * kb, ld, 128, 64, 0);            // feature columns
+    add(p, r, kF, ld, 128, kV, 0);                                                // view columns
+  });
+  // ---- dgrad chain: dst(n = input feature, k = output feature); per layer, per N-half of the INPUT features
   off = (uint32_t)kPackedBwdOff;
-  for (int kb = 0; kb < 2; ++kb) add(W_9, 64 * kb, 0, kF + kV, kF, 64, 1);      // fc_9^T, feature inputs only
-  for (int kb = 0; kb < 4; ++kb) add(W_8, 1 + 64 * kb, 0, kF, kF, 64, 1);       // fc_8^T, feature rows
-  for (int kb = 0; kb < 4; ++kb) add(W_7, 64 * kb, 0, kF, kF, 64, 1);
-  for (int kb = 0; kb < 4; ++kb) add(W_6, 64 * kb, 0, kF, kF, 64, 1);
-  for (int kb = 0; kb < 4; ++kb) add(W_5, 64 * kb, kP, kP + kF, kF, 64, 1);     // fc_5^T, h4 columns only
-  for (int l = 4; l >= 1; --l)
-    for (int kb = 0; kb < 4; ++kb) add(2 * l, 64 * kb, 0, kF, kF, 64, 1);       // fc_4^T .. fc_1^T
+  auto bwd_layer = [&](int param, int out_row0, int in_col0, int ld, int nk) {
+    for (int nh = 0; nh < 2; ++nh)
+      for (int kb = 0; kb < nk; ++kb) add(param, out_row0 + 64 * kb, in_col0 + 128 * nh, ld, 128, 64, 1);
+  };
+  bwd_layer(W_9, 0, 0, kF + kV, 2);       // fc_9^T, feature inputs only (128 outputs -> 2 K chunks)
+  bwd_layer(W_8, 1, 0, kF, 4);            // fc_8^T, feature rows
+  bwd_layer(W_7, 0, 0, kF, 4);
+  bwd_layer(W_6, 0, 0, kF, 4);
+  bwd_layer(W_5, 0, kP, kP + kF, 4);      // fc_5^T, h4 columns only
+  for (int l = 4; l >= 1; --l) bwd_layer(2 * l, 0, 0, kF, 4);
   return n;
 }
 
@@ -115,7 +125,7 @@ int nerf_mlp_bf16_pack(const float* const* params, void* packed_dev, nerf_stream
     NERF_CHECK_ARG(params[i] != nullptr, "nerf_mlp_bf16_pack: null parameter pointer");
     pp.p[i] = const_cast<float*>(params[i]);
   }
-  dim3 grid((kF * 8 + 255) / 256, g_pack_chunks);
+  dim3 grid((128 * 8 + 255) / 256, g_pack_chunks);
   pack_weights_kernel<<<grid, 256, 0, st>>>(pp, reinterpret_cast<uint8_t*>(packed_dev));
   NERF_LAUNCH_CHECK();
   pack_consts_kernel<<<(kCFloats + 255) / 256, 256, 0, st>>>(

@@ -11,6 +11,8 @@ using namespace tc;
 // ------------------------------------------------------------------------------------------------
 // variant 0: a (128 x k) row-major, b (n x k) row-major        -> K-major images
 // variant 1: a (k x 128) row-major (= A^T), b (k x n) row-major -> MN-major images (the wgrad form)
+// variant 2: like 0, but the A operand is first written to TMEM with tcgen05.st (packed bf16 pairs, row = lane)
+//            and the MMAs use the TS form (A from tensor memory) -- the chain kernels' operand path
 __global__ void __launch_bounds__(128, 1) selftest_umma_kernel(const uint16_t* __restrict__ a,
                                                                const uint16_t* __restrict__ b, float* __restrict__ d,
                                                                int n, int k, int variant) {
@@ -23,7 +25,7 @@ __global__ void __launch_bounds__(128, 1) selftest_umma_kernel(const uint16_t* _
   uint8_t* sA;
   uint8_t* sB;
   uint32_t a_blk, b_blk;  // byte stride between 64-column blocks
-  if (variant == 0) {
+  if (variant == 0 || variant == 2) {
     a_blk = 128 * 128;
     b_blk = n * 128;
     sA = smem;
@@ -55,15 +57,36 @@ __global__ void __launch_bounds__(128, 1) selftest_umma_kernel(const uint16_t* _
     mbar_init(&bar, 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  if (variant == 2) {
+    // row = TMEM lane; 64 bf16 (one k-block) = 32 packed words = 32 TMEM columns at [256 + 32*kb, +32)
+    const int row = warp * 32 + lane;
+    for (int kb = 0; kb < nkb; ++kb) {
+      uint32_t w[32];
+      for (int c = 0; c < 32; ++c) {
+        const uint32_t lo = a[(size_t)row * k + kb * 64 + 2 * c], hi = a[(size_t)row * k + kb * 64 + 2 * c + 1];
+        w[c] = lo | (hi << 16);
+      }
+      tmem_st32(tmem_base + ((uint32_t)(warp * 32) << 16) + 256 + kb * 32, w);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
   if (threadIdx.x == 0) {
     const uint32_t idesc = make_idesc_bf16((uint32_t)n, variant == 1, variant == 1);
     for (int kk = 0; kk < k / 16; ++kk) {
       uint64_t da, db;
+      if (variant == 2) {
+        db = desc_kmajor(smem_u32(sB) + (kk / 4) * b_blk + (kk % 4) * 32);
+        umma_bf16_ts(tmem_base, tmem_base + 256 + 8 * kk, db, idesc, kk > 0 ? 1u : 0u);
+        continue;
+      }
       if (variant == 0) {
         da = desc_kmajor(smem_u32(sA) + (kk / 4) * a_blk + (kk % 4) * 32);
         db = desc_kmajor(smem_u32(sB) + (kk / 4) * b_blk + (kk % 4) * 32);
@@ -86,7 +109,7 @@ __global__ void __launch_bounds__(128, 1) selftest_umma_kernel(const uint16_t* _
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 256);
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
 
@@ -95,17 +118,6 @@ __global__ void __launch_bounds__(128, 1) selftest_umma_kernel(const uint16_t* _
 //   mode 0: A and B from shared memory (SS), N = n;   mode 1: A from TMEM (TS), B from shared memory
 // out[block] = cycles for `iters` groups of 4 MMAs (one 64-wide k-block), measured by the issuing thread.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
-                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      :
-      : "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
 __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, int n, int mode, unsigned long long* out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -154,8 +166,8 @@ extern "C" {
 int nerf_selftest_umma(const uint16_t* a_dev, const uint16_t* b_dev, float* d_dev, int n, int k, int variant,
                        nerf_stream_t stream) {
   NERF_CHECK_ARG(a_dev && b_dev && d_dev, "nerf_selftest_umma: null pointer");
-  NERF_CHECK_ARG(n >= 64 && n <= 256 && n % 64 == 0 && k >= 64 && k <= 256 && k % 64 == 0 && (variant == 0 || variant == 1),
-                 "nerf_selftest_umma: n, k must be multiples of 64 in [64,256]; variant 0|1");
+  NERF_CHECK_ARG(n >= 64 && n <= 256 && n % 64 == 0 && k >= 64 && k <= 256 && k % 64 == 0 && (variant >= 0 && variant <= 2),
+                 "nerf_selftest_umma: n, k must be multiples of 64 in [64,256]; variant 0|1|2");
   size_t smem = (size_t)128 * k * 2 + (size_t)n * k * 2 + 1024;
   NERF_CUDA(cudaFuncSetAttribute(selftest_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   selftest_umma_kernel<<<1, 128, smem, as_stream(stream)>>>(a_dev, b_dev, d_dev, n, k, variant);
