@@ -6,16 +6,30 @@ import torch_nerf_b200 as tn
 
 lib = tn._lib.load()
 P, VP = tn._lib.ptr, tn._lib.c_void_p
-out = torch.zeros(148, dtype=torch.int64, device="cuda")
-for blocks in (148,):
-    for mode, n in ((0, 256), (0, 128), (0, 64), (1, 256), (1, 128)):
-        iters = 2000
-        tn._lib.check(lib.nerf_selftest_mma_rate(blocks, iters, n, mode, VP(out.data_ptr()), tn._lib.stream()), "rate")
-        torch.cuda.synchronize()
-        cyc = out[:blocks].float()
-        per = cyc / (iters * 4)
-        print(f"mma_rate blocks={blocks:3d} mode={'SS' if mode == 0 else 'TS'} N={n:3d}: cycles/MMA mean {per.mean():.1f} max {per.max():.1f}  "
-              f"(floor {128 * n / 256:.0f})")
+out = torch.zeros(2 * 148, dtype=torch.int64, device="cuda")
+def rate(blocks, iters, n, mode, bg_warps=0, bg_iters=0, bg_store=0):
+    out.zero_()
+    tn._lib.check(lib.nerf_selftest_mma_rate(blocks, iters, n, mode, bg_warps, bg_iters, bg_store, VP(out.data_ptr()), tn._lib.stream()), "rate")
+    torch.cuda.synchronize()
+    mma = out[:blocks].float().mean().item() / max(1, iters * 4)
+    bg = out[blocks:2 * blocks].float().mean().item() / max(1, bg_iters)
+    return mma, bg
+if "--micro" in sys.argv:
+    for mode, n in ((0, 256), (0, 128), (1, 256), (1, 128)):
+        m, _ = rate(148, 2000, n, mode)
+        print(f"mma alone   mode={'SS' if mode == 0 else 'TS'} N={n:3d}: {m:6.1f} cycles/MMA (floor {128 * n / 256:.0f})")
+    for w in (1, 4, 8, 16):
+        _, l = rate(148, 0, 128, 0, w, 4000, 0)
+        _, st = rate(148, 0, 128, 0, w, 4000, 1)
+        print(f"tmem alone  {w:2d} warps: ld {l:6.1f} cycles per 32x32 fp32 load per warp -> {w * 4096 / l:6.1f} B/cycle/SM ; "
+              f"st {st:6.1f} cycles -> {w * 4096 / st:6.1f} B/cycle/SM")
+    for mode, n in ((0, 256), (1, 128), (0, 128)):
+        for w in (4, 8):
+            for store in (0, 1):
+                m, l = rate(148, 2000, n, mode, w, 100000, store)  # background runs longer than the MMAs
+                m2, l2 = rate(148, 2000, n, mode, w, 2000, store)
+                print(f"mma + {w} warps of tmem {'st' if store else 'ld'}  mode={'SS' if mode == 0 else 'TS'} N={n:3d}: {m:6.1f} cycles/MMA")
+    sys.exit(0)
 
 n, s = 4096, 192
 m = n * s

@@ -112,22 +112,28 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
   const float* sWout = sC + 256;  // fc_out.weight (3,128)
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       uint32_t g = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint8_t* src = a.packed + kPackedBwdOff;
         for (int c = 0; c < kBwdChunks; ++c) {
           const uint32_t s = g % kDgStages, ph = (g / kDgStages) & 1;
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full[s], kDgStageBytes);
-          bulk_g2s(sW + s * kDgStageBytes, src, kDgStageBytes, &full[s]);
+          if (leader) {
+            mbar_arrive_expect_tx(&full[s], kDgStageBytes);
+            bulk_g2s(sW + s * kDgStageBytes, src, kDgStageBytes, &full[s]);
+          }
+          __syncwarp();
           src += kDgStageBytes;
           ++g;
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // the whole warp runs the issue loop in lock step; one elected lane issues (keeps descriptors in uniform registers)
+    {
+      const bool leader = elect_one();
       uint32_t g = 0;
       uint32_t a_cnt[4] = {0, 0, 0, 0};
       constexpr uint32_t idesc = make_idesc_bf16(128, false, false);
@@ -154,13 +160,17 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
               mbar_wait(&full[s], ph);
               tc_fence_after();
               const uint64_t db = desc_kmajor(sW_u + s * kDgStageBytes);
+              if (leader) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16_ts(acc, a_tm + (uint32_t)(kb * 32 + k * 8), db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-              umma_commit(&empty[s]);
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16_ts(acc, a_tm + (uint32_t)(kb * 32 + k * 8), db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&empty[s]);
+              }
+              __syncwarp();
               ++g;
             }
-            umma_commit(&acc_full[nh]);
+            if (leader) umma_commit(&acc_full[nh]);
+            __syncwarp();
           }
         }
       }
@@ -392,7 +402,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
 
   if (warp == 0) {
     // ------------------------------------------------------------------ loader: 32-row slices of every block
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       uint32_t g = 0;
       const uint8_t* ghead = a.scratch + scratch_ghead_offset(a.m);
       for (int si = 0; si < nseg; ++si) {
@@ -405,16 +416,19 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
           for (int sl = 0; sl < 4; ++sl) {
             const uint32_t s = g % kWgStages, ph = (g / kWgStages) & 1;
             mbar_wait(&empty[s], ph ^ 1);
-            mbar_arrive_expect_tx(&full[s], bytes);
-            uint8_t* dst = smem + s * kWgStageBytes;
-            for (int b = 0; b < u.n_gblk; ++b)
-              bulk_g2s(dst + b * kWgSlice, gsrc + (size_t)b * kBlockBytes + sl * kWgSlice, kWgSlice, &full[s]);
-            uint8_t* xdst = dst + u.n_gblk * kWgSlice;
-            for (int b = 0; b < u.n_xblk; ++b)
-              bulk_g2s(xdst + b * kWgSlice, xsrc + (size_t)(u.x_blk0 + b) * kBlockBytes + sl * kWgSlice, kWgSlice, &full[s]);
-            if (u.x_extra >= 0)
-              bulk_g2s(xdst + u.n_xblk * kWgSlice, xsrc + (size_t)u.x_extra * kBlockBytes + sl * kWgSlice, kWgSlice, &full[s]);
-            if (u.head) bulk_g2s(dst + kWgHeadOff, ghead + ((size_t)tile * kTileM + sl * 32) * 16, 512, &full[s]);
+            if (leader) {
+              mbar_arrive_expect_tx(&full[s], bytes);
+              uint8_t* dst = smem + s * kWgStageBytes;
+              for (int b = 0; b < u.n_gblk; ++b)
+                bulk_g2s(dst + b * kWgSlice, gsrc + (size_t)b * kBlockBytes + sl * kWgSlice, kWgSlice, &full[s]);
+              uint8_t* xdst = dst + u.n_gblk * kWgSlice;
+              for (int b = 0; b < u.n_xblk; ++b)
+                bulk_g2s(xdst + b * kWgSlice, xsrc + (size_t)(u.x_blk0 + b) * kBlockBytes + sl * kWgSlice, kWgSlice, &full[s]);
+              if (u.x_extra >= 0)
+                bulk_g2s(xdst + u.n_xblk * kWgSlice, xsrc + (size_t)u.x_extra * kBlockBytes + sl * kWgSlice, kWgSlice, &full[s]);
+              if (u.head) bulk_g2s(dst + kWgHeadOff, ghead + ((size_t)tile * kTileM + sl * 32) * 16, 512, &full[s]);
+            }
+            __syncwarp();
             ++g;
           }
         }
@@ -422,7 +436,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (MN-major operands)
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       uint32_t g = 0;
       const uint32_t sm_u = smem_u32(smem);
       for (int si = 0; si < nseg; ++si) {
@@ -441,24 +456,28 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
             tc_fence_after();
             const uint32_t st = sm_u + s * kWgStageBytes;
             const uint32_t xb = st + u.n_gblk * kWgSlice;
+            if (leader) {
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              for (int h = 0; h < nhalf; ++h) {
-                const uint64_t da = desc_mnmajor(st + (2 * h) * kWgSlice + k * 2048, kWgSlice);
-                const uint64_t db = desc_mnmajor(xb + k * 2048, kWgSlice);
-                umma_bf16(tmem_base + h * 256, da, db, idesc_main, first ? 0u : 1u);
-                if (u.x_extra >= 0) {
-                  const uint64_t de = desc_mnmajor(xb + u.n_xblk * kWgSlice + k * 2048, kWgSlice);
-                  umma_bf16(tmem_base + h * 256 + n_main, da, de, idesc_extra, first ? 0u : 1u);
+              for (int k = 0; k < 2; ++k) {
+                for (int h = 0; h < nhalf; ++h) {
+                  const uint64_t da = desc_mnmajor(st + (2 * h) * kWgSlice + k * 2048, kWgSlice);
+                  const uint64_t db = desc_mnmajor(xb + k * 2048, kWgSlice);
+                  umma_bf16(tmem_base + h * 256, da, db, idesc_main, (first && k == 0) ? 0u : 1u);
+                  if (u.x_extra >= 0) {
+                    const uint64_t de = desc_mnmajor(xb + u.n_xblk * kWgSlice + k * 2048, kWgSlice);
+                    umma_bf16(tmem_base + h * 256 + n_main, da, de, idesc_extra, (first && k == 0) ? 0u : 1u);
+                  }
                 }
               }
-              first = false;
+              umma_commit(&empty[s]);
             }
-            umma_commit(&empty[s]);
+            first = false;
+            __syncwarp();
             ++g;
           }
         }
-        umma_commit(acc_done);
+        if (leader) umma_commit(acc_done);
+        __syncwarp();
       }
     }
   } else {

@@ -180,16 +180,20 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ weight loader
-    if (lane == 0) {
+    // ------------------------------------------------------------------ weight loader (warp in lock step, one lane issues)
+    {
+      const bool leader = elect_one();
       uint32_t g = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint8_t* src = a.packed + kPackedFwdOff;
         for (int c = 0; c < kFwdChunks; ++c) {
           const uint32_t s = g % kStages, ph = (g / kStages) & 1;
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full[s], kStageBytes);
-          bulk_g2s(sW + s * kStageBytes, src, kStageBytes, &full[s]);
+          if (leader) {
+            mbar_arrive_expect_tx(&full[s], kStageBytes);
+            bulk_g2s(sW + s * kStageBytes, src, kStageBytes, &full[s]);
+          }
+          __syncwarp();
           src += kStageBytes;
           ++g;
         }
@@ -197,7 +201,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp runs this loop in lock step (waits included); one elected lane issues.
+    {
+      const bool leader = elect_one();
       uint32_t g = 0, a_cnt = 0, in_cnt = 0;
       constexpr uint32_t idesc = make_idesc_bf16(128, false, false);
       const uint32_t sIn_u = smem_u32(sIn), sW_u = smem_u32(sW);
@@ -209,7 +215,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
           const int nk = fwd_nk(l);
           const uint32_t a_tm = tmem_base + kTmA + (uint32_t)(l & 1) * 128u;  // this layer's A operand in TMEM
           const bool stamp = a.prof != nullptr && blockIdx.x == 0 && (int)in_cnt <= a.prof_tiles;
-          if (stamp) a.prof[(((int)in_cnt - 1) * kNumFwdLayers + l) * 8 + 0] = clock64();
+          if (stamp && leader) a.prof[(((int)in_cnt - 1) * kNumFwdLayers + l) * 8 + 0] = clock64();
           long long wait_a = 0, wait_w = 0;
           // a_ready[b] completes once per producing layer 0..8; layer l >= 1 consumes round (l - 1)
           const uint32_t a_par = (a_cnt + (uint32_t)(l - 1)) & 1;
@@ -245,21 +251,25 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
               if (stamp) wait_w += clock64() - w1;
               tc_fence_after();
               const uint64_t db = desc_kmajor(sW_u + s * kStageBytes);
-              if (ab >= 0) {
+              if (leader) {
+                if (ab >= 0) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16_ts(acc, a_tm + (uint32_t)(ab * 32 + k * 8), db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-              } else {
-                const uint64_t da = desc_kmajor(a_smem);
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16_ts(acc, a_tm + (uint32_t)(ab * 32 + k * 8), db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                } else {
+                  const uint64_t da = desc_kmajor(a_smem);
 #pragma unroll 4
-                for (int k = 0; k < nsteps; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                  for (int k = 0; k < nsteps; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty[s]);
               }
-              umma_commit(&empty[s]);
+              __syncwarp();
               ++g;
             }
-            umma_commit(&acc_full[nh]);
+            if (leader) umma_commit(&acc_full[nh]);
+            __syncwarp();
           }
-          if (stamp) {
+          if (stamp && leader) {
             unsigned long long* pr = a.prof + (((int)in_cnt - 1) * kNumFwdLayers + l) * 8;
             pr[1] = clock64();
             pr[4] = (unsigned long long)wait_a;

@@ -118,13 +118,17 @@ __global__ void __launch_bounds__(128, 1) selftest_umma_kernel(const uint16_t* _
 //   mode 0: A and B from shared memory (SS), N = n;   mode 1: A from TMEM (TS), B from shared memory
 // out[block] = cycles for `iters` groups of 4 MMAs (one 64-wide k-block), measured by the issuing thread.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, int n, int mode, unsigned long long* out) {
+// bg_warps extra warps stream tcgen05.ld (32x32b.x32 of the accumulator region) or tcgen05.st concurrently, to
+// measure how epilogue traffic and the MMA pipe share tensor memory.  out[block] = MMA-thread cycles,
+// out[gridDim.x + block] = cycles of the first background warp for its `bg_iters` accesses.
+__global__ void __launch_bounds__(640, 1) mma_rate_kernel(int iters, int n, int mode, int bg_warps, int bg_iters, int bg_store,
+                                                           unsigned long long* out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
-  const int warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
   fence_proxy_async();
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
@@ -135,7 +139,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, int n, int 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && iters > 0) {
     const uint32_t idesc = make_idesc_bf16((uint32_t)n, false, false);
     const uint64_t da = desc_kmajor(smem_u32(smem));
     const uint64_t db = desc_kmajor(smem_u32(smem) + 16384);
@@ -151,6 +155,27 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, int n, int 
     mbar_wait(&bar, 0);
     const long long t1 = clock64();
     out[blockIdx.x] = (unsigned long long)(t1 - t0);
+  }
+  if (warp >= 4 && warp < 4 + bg_warps) {
+    // background tensor-memory traffic on columns [384,512) (not touched by the MMAs)
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 384;
+    uint32_t v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = lane + i;
+    uint32_t acc = 0;
+    const long long t0 = clock64();
+    for (int it = 0; it < bg_iters; ++it) {
+      if (bg_store) {
+        tmem_st32(taddr + (it & 3) * 32, v);
+        tmem_st_wait();
+      } else {
+        tmem_ld32(taddr + (it & 3) * 32, v);
+        tmem_ld_wait();
+        acc ^= v[it & 31];
+      }
+    }
+    const long long t1 = clock64();
+    if (warp == 4 && lane == 0) out[gridDim.x + blockIdx.x] = (unsigned long long)(t1 - t0) + (acc & 0u);
   }
   tc_fence_before();
   __syncthreads();
@@ -175,12 +200,15 @@ int nerf_selftest_umma(const uint16_t* a_dev, const uint16_t* b_dev, float* d_de
   return NERF_OK;
 }
 
-int nerf_selftest_mma_rate(int blocks, int iters, int n, int mode, unsigned long long* cycles_dev, nerf_stream_t stream) {
-  NERF_CHECK_ARG(cycles_dev && blocks > 0 && iters > 0 && n >= 16 && n <= 256 && n % 16 == 0 && (mode == 0 || mode == 1),
+int nerf_selftest_mma_rate(int blocks, int iters, int n, int mode, int bg_warps, int bg_iters, int bg_store,
+                           unsigned long long* cycles_dev, nerf_stream_t stream) {
+  NERF_CHECK_ARG(cycles_dev && blocks > 0 && iters >= 0 && n >= 16 && n <= 256 && n % 16 == 0 && (mode == 0 || mode == 1) &&
+                     bg_warps >= 0 && bg_warps <= 16 && bg_iters >= 0,
                  "nerf_selftest_mma_rate: bad arguments");
   const size_t smem = 16384 + 32768 + 1024;
   NERF_CUDA(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  mma_rate_kernel<<<blocks, 128, smem, as_stream(stream)>>>(iters, n, mode, cycles_dev);
+  mma_rate_kernel<<<blocks, 128 + 32 * bg_warps, smem, as_stream(stream)>>>(iters, n, mode, bg_warps, bg_iters, bg_store,
+                                                                              cycles_dev);
   NERF_LAUNCH_CHECK();
   return NERF_OK;
 }

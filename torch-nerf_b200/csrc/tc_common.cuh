@@ -79,6 +79,19 @@ __device__ __forceinline__ void bulk_wait_all() {
 // generic-proxy writes to shared memory -> visible to the async proxy (UMMA operand reads, bulk stores)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// one lane of a converged warp (elect.sync); the tcgen05.mma / commit issue sites are guarded by this predicate inside
+// warp-uniform control flow so that ptxas keeps the descriptors in uniform registers instead of emitting a
+// per-instruction ELECT / BRA.U.ANY waterfall (which made MMA issue, not the tensor pipe, the bottleneck)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
