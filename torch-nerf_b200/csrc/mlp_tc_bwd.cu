@@ -131,48 +131,75 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
       }
     }
   } else if (warp == 1) {
-    // the whole warp runs the issue loop in lock step; one elected lane issues (keeps descriptors in uniform registers)
+    // MMA issuer: the whole warp runs the loop in lock step, one elected lane issues; a step's barriers are polled
+    // while the previous step's MMAs execute (see mlp_tc_fwd.cu)
     {
       const bool leader = elect_one();
-      uint32_t g = 0;
-      uint32_t a_cnt[4] = {0, 0, 0, 0};
       constexpr uint32_t idesc = make_idesc_bf16(128, false, false);
       const uint32_t sW_u = smem_u32(sW);
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int j = 0; j < kNumBwdLayers; ++j) {
-          const int nk = bwd_nk(j);
-          const uint32_t a_tm = tmem_base + kDgTmA + (uint32_t)(j & 1) * 128u;  // this layer's A operand (G) in TMEM
-          // N-half 0 overwrites accumulator columns [0,128): both warp groups must have drained them, which each
-          // signals through its first gradient block (for j == 0: the G9 blocks, written after the previous tile)
-          mbar_wait(&a_ready[0], a_cnt[0] & 1);
-          mbar_wait(&a_ready[1], a_cnt[1] & 1);
-          ++a_cnt[0];
-          ++a_cnt[1];
-          for (int nh = 0; nh < 2; ++nh) {
-            const uint32_t acc = tmem_base + (uint32_t)nh * 128u;
-#pragma unroll 1
-            for (int kb = 0; kb < nk; ++kb) {
-              if (nh == 0 && kb >= 2) {
-                mbar_wait(&a_ready[kb], a_cnt[kb] & 1);
-                ++a_cnt[kb];
-              }
-              const uint32_t s = g % kDgStages, ph = (g / kDgStages) & 1;
-              mbar_wait(&full[s], ph);
-              tc_fence_after();
-              const uint64_t db = desc_kmajor(sW_u + s * kDgStageBytes);
-              if (leader) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16_ts(acc, a_tm + (uint32_t)(kb * 32 + k * 8), db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                umma_commit(&empty[s]);
-              }
-              __syncwarp();
-              ++g;
+      struct Step {
+        int64_t tile;
+        int j, nh, kb;
+        uint32_t g, tile_iter;
+      };
+      auto advance = [&](Step& st) {
+        ++st.g;
+        if (++st.kb == bwd_nk(st.j)) {
+          st.kb = 0;
+          if (++st.nh == 2) {
+            st.nh = 0;
+            if (++st.j == kNumBwdLayers) {
+              st.j = 0;
+              st.tile += gridDim.x;
+              ++st.tile_iter;
             }
-            if (leader) umma_commit(&acc_full[nh]);
-            __syncwarp();
           }
         }
+      };
+      auto first_of_tile = [](const Step& st) { return st.j == 0 && st.nh == 0 && st.kb == 0; };
+      auto wait_for = [&](const Step& st) {
+        if (st.nh == 0) {
+          if (st.kb == 0) {
+            // N-half 0 overwrites accumulator columns [0,128): both warp groups must have drained them, which each
+            // signals through its first gradient block (j == 0: the G9 blocks, written after the previous tile).
+            // a_ready[0], [1] complete 9 times per tile (input stage + layers 0..7), layer j consumes round j.
+            const uint32_t par = (st.tile_iter + (uint32_t)st.j) & 1;
+            mbar_wait(&a_ready[0], par);
+            mbar_wait(&a_ready[1], par);
+          } else if (st.kb >= 2) {
+            // a_ready[2], [3] complete 8 times per tile (layers 0..7), layer j >= 1 consumes round j - 1
+            mbar_wait(&a_ready[st.kb], (uint32_t)(st.j - 1) & 1);
+          }
+        }
+        mbar_wait(&full[st.g % kDgStages], (st.g / kDgStages) & 1);
+        tc_fence_after();
+      };
+      auto issue = [&](const Step& st, int half) {
+        const uint32_t acc = tmem_base + (uint32_t)st.nh * 128u;
+        const uint32_t a_tm = tmem_base + kDgTmA + (uint32_t)(st.j & 1) * 128u + (uint32_t)st.kb * 32u;
+        const uint64_t db = desc_kmajor(sW_u + (st.g % kDgStages) * kDgStageBytes);
+#pragma unroll
+        for (int k = 2 * half; k < 2 * half + 2; ++k)
+          umma_bf16_ts(acc, a_tm + (uint32_t)k * 8u, db + 2 * k, idesc, (st.kb > 0 || k > 0) ? 1u : 0u);
+      };
+      Step cur{(int64_t)blockIdx.x, 0, 0, 0, 0u, 0u};
+      if (cur.tile < ntiles) wait_for(cur);
+      while (cur.tile < ntiles) {
+        Step nxt = cur;
+        advance(nxt);
+        const bool nxt_valid = nxt.tile < ntiles;
+        if (leader) issue(cur, 0);
+        __syncwarp();
+        // look ahead -- except across a tile boundary: the next tile's G9 blocks depend on this step's commit
+        if (nxt_valid && !first_of_tile(nxt)) wait_for(nxt);
+        if (leader) {
+          issue(cur, 1);
+          umma_commit(&empty[cur.g % kDgStages]);
+          if (cur.kb == bwd_nk(cur.j) - 1) umma_commit(&acc_full[cur.nh]);
+        }
+        __syncwarp();
+        if (nxt_valid && first_of_tile(nxt)) wait_for(nxt);
+        cur = nxt;
       }
     }
   } else {

@@ -201,82 +201,102 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    // The whole warp runs this loop in lock step (waits included); one elected lane issues.
+    // The whole warp runs this loop in lock step (waits included); one elected lane issues.  The schedule is a flat
+    // sequence of steps (tile, layer l, N-half nh, k-chunk kb).  A step's barriers are polled while the previous
+    // step's MMAs are still executing (issue first half -> poll next step's barriers -> issue second half -> commit):
+    // an mbarrier probe costs ~150 cycles even when the phase is already complete and the MMA queue is shallow, so
+    // polling between steps would starve the tensor pipe on every chunk.
     {
       const bool leader = elect_one();
-      uint32_t g = 0, a_cnt = 0, in_cnt = 0;
       constexpr uint32_t idesc = make_idesc_bf16(128, false, false);
       const uint32_t sIn_u = smem_u32(sIn), sW_u = smem_u32(sW);
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        // the encoded inputs are ready; all epilogue warps have also left the previous tile (accumulator drained)
-        mbar_wait(in_ready, in_cnt & 1);
-        ++in_cnt;
-        for (int l = 0; l < kNumFwdLayers; ++l) {
-          const int nk = fwd_nk(l);
-          const uint32_t a_tm = tmem_base + kTmA + (uint32_t)(l & 1) * 128u;  // this layer's A operand in TMEM
-          const bool stamp = a.prof != nullptr && blockIdx.x == 0 && (int)in_cnt <= a.prof_tiles;
-          if (stamp && leader) a.prof[(((int)in_cnt - 1) * kNumFwdLayers + l) * 8 + 0] = clock64();
-          long long wait_a = 0, wait_w = 0;
-          // a_ready[b] completes once per producing layer 0..8; layer l >= 1 consumes round (l - 1)
-          const uint32_t a_par = (a_cnt + (uint32_t)(l - 1)) & 1;
-          if (l >= 1) {
-            // N-half 0 overwrites accumulator columns [0,128): both warp groups must have drained them
-            const long long w0 = stamp ? clock64() : 0;
-            mbar_wait(&a_ready[0], a_par);
-            mbar_wait(&a_ready[1], a_par);
-            if (stamp) wait_a += clock64() - w0;
-          }
-          for (int nh = 0; nh < fwd_nh(l); ++nh) {
-            const uint32_t acc = tmem_base + kTmAcc + (uint32_t)nh * 128u;
-            for (int kb = 0; kb < nk; ++kb) {
-              int ab = -1;             // A k-block in TMEM, or -1 for the shared-memory blocks
-              uint32_t a_smem = 0;
-              int nsteps = 4;
-              if (l == 0 || (l == 5 && kb == 0)) {
-                a_smem = sIn_u;                      // encoded position
-              } else if (l == 9 && kb == 4) {
-                a_smem = sIn_u + kBlockBytes;        // encoded view direction (K = 32)
-                nsteps = 2;
-              } else {
-                ab = (l == 5) ? kb - 1 : kb;
-                if (nh == 0 && ab >= 2) {
-                  const long long w0 = stamp ? clock64() : 0;
-                  mbar_wait(&a_ready[ab], a_par);
-                  if (stamp) wait_a += clock64() - w0;
-                }
-              }
-              const uint32_t s = g % kStages, ph = (g / kStages) & 1;
-              const long long w1 = stamp ? clock64() : 0;
-              mbar_wait(&full[s], ph);
-              if (stamp) wait_w += clock64() - w1;
-              tc_fence_after();
-              const uint64_t db = desc_kmajor(sW_u + s * kStageBytes);
-              if (leader) {
-                if (ab >= 0) {
-#pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    umma_bf16_ts(acc, a_tm + (uint32_t)(ab * 32 + k * 8), db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                } else {
-                  const uint64_t da = desc_kmajor(a_smem);
-#pragma unroll 4
-                  for (int k = 0; k < nsteps; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                }
-                umma_commit(&empty[s]);
-              }
-              __syncwarp();
-              ++g;
+      struct Step {
+        int64_t tile;
+        int l, nh, kb;
+        uint32_t g, tile_iter;
+      };
+      auto advance = [&](Step& st) {
+        ++st.g;
+        if (++st.kb == fwd_nk(st.l)) {
+          st.kb = 0;
+          if (++st.nh == fwd_nh(st.l)) {
+            st.nh = 0;
+            if (++st.l == kNumFwdLayers) {
+              st.l = 0;
+              st.tile += gridDim.x;
+              ++st.tile_iter;
             }
-            if (leader) umma_commit(&acc_full[nh]);
-            __syncwarp();
-          }
-          if (stamp && leader) {
-            unsigned long long* pr = a.prof + (((int)in_cnt - 1) * kNumFwdLayers + l) * 8;
-            pr[1] = clock64();
-            pr[4] = (unsigned long long)wait_a;
-            pr[5] = (unsigned long long)wait_w;
           }
         }
-        a_cnt += 9;
+      };
+      auto first_of_tile = [](const Step& st) { return st.l == 0 && st.nh == 0 && st.kb == 0; };
+      // k-block of the TMEM A buffer this step reads, or -1 when its A operand is one of the shared-memory blocks
+      auto a_block = [](const Step& st) {
+        if (st.l == 0 || (st.l == 5 && st.kb == 0) || (st.l == 9 && st.kb == 4)) return -1;
+        return st.l == 5 ? st.kb - 1 : st.kb;
+      };
+      auto wait_for = [&](const Step& st) {
+        if (first_of_tile(st)) {
+          // encoded inputs ready; every epilogue warp has also left the previous tile (accumulator drained)
+          mbar_wait(in_ready, st.tile_iter & 1);
+        }
+        if (st.l >= 1 && st.nh == 0) {
+          // a_ready[b] completes once per producing layer 0..8 (9 per tile); layer l consumes round l - 1
+          const uint32_t a_par = (st.tile_iter + (uint32_t)(st.l - 1)) & 1;
+          if (st.kb == 0) {
+            // N-half 0 overwrites accumulator columns [0,128): both warp groups must have drained them
+            mbar_wait(&a_ready[0], a_par);
+            mbar_wait(&a_ready[1], a_par);
+          }
+          const int ab = a_block(st);
+          if (ab >= 2) mbar_wait(&a_ready[ab], a_par);
+        }
+        mbar_wait(&full[st.g % kStages], (st.g / kStages) & 1);
+        tc_fence_after();
+      };
+      auto issue = [&](const Step& st, int half) {
+        const uint32_t acc = tmem_base + kTmAcc + (uint32_t)st.nh * 128u;
+        const uint64_t db = desc_kmajor(sW_u + (st.g % kStages) * kStageBytes);
+        const int ab = a_block(st);
+        if (ab >= 0) {
+          const uint32_t a_tm = tmem_base + kTmA + (uint32_t)(st.l & 1) * 128u + (uint32_t)ab * 32u;
+#pragma unroll
+          for (int k = 2 * half; k < 2 * half + 2; ++k)
+            umma_bf16_ts(acc, a_tm + (uint32_t)k * 8u, db + 2 * k, idesc, (st.kb > 0 || k > 0) ? 1u : 0u);
+        } else {
+          const bool view = (st.l == 9);  // encoded view direction: K = 32 (two MMAs), else encoded position (four)
+          const uint64_t da = desc_kmajor(view ? sIn_u + kBlockBytes : sIn_u);
+          if (view) {
+            umma_bf16(acc, da + 2 * half, db + 2 * half, idesc, 1u);
+          } else {
+#pragma unroll
+            for (int k = 2 * half; k < 2 * half + 2; ++k)
+              umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (st.kb > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+      };
+      Step cur{(int64_t)blockIdx.x, 0, 0, 0, 0u, 0u};
+      if (cur.tile < ntiles) wait_for(cur);
+      while (cur.tile < ntiles) {
+        Step nxt = cur;
+        advance(nxt);
+        const bool nxt_valid = nxt.tile < ntiles;
+        const bool stamp = a.prof != nullptr && blockIdx.x == 0 && (int)cur.tile_iter < a.prof_tiles && leader;
+        if (stamp && cur.nh == 0 && cur.kb == 0) a.prof[(cur.tile_iter * kNumFwdLayers + cur.l) * 8 + 0] = clock64();
+        if (leader) issue(cur, 0);
+        __syncwarp();
+        // look ahead -- except across a tile boundary: in_ready of the next tile depends on this step's commit
+        if (nxt_valid && !first_of_tile(nxt)) wait_for(nxt);
+        if (leader) {
+          issue(cur, 1);
+          umma_commit(&empty[cur.g % kStages]);
+          if (cur.kb == fwd_nk(cur.l) - 1) umma_commit(&acc_full[cur.nh]);
+        }
+        __syncwarp();
+        if (stamp && cur.kb == fwd_nk(cur.l) - 1 && cur.nh == fwd_nh(cur.l) - 1)
+          a.prof[(cur.tile_iter * kNumFwdLayers + cur.l) * 8 + 1] = clock64();
+        if (nxt_valid && first_of_tile(nxt)) wait_for(nxt);
+        cur = nxt;
       }
     }
   } else {
