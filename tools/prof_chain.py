@@ -18,6 +18,12 @@ if "--micro" in sys.argv:
     for mode, n in ((0, 256), (0, 128), (1, 256), (1, 128)):
         m, _ = rate(148, 2000, n, mode)
         print(f"mma alone   mode={'SS' if mode == 0 else 'TS'} N={n:3d}: {m:6.1f} cycles/MMA (floor {128 * n / 256:.0f})")
+    for n in (128, 256):
+        for flags, label in ((2, "commit per 4"), (4, "probe per 4"), (6, "commit+probe per 4"), (8, "syncwarp per 4"), (14, "all three")):
+            m, _ = rate(148, 2000, n, 1 | flags)
+            print(f"mma TS N={n:3d} + {label:20s}: {m:6.1f} cycles/MMA")
+    if "--short" in sys.argv:
+        sys.exit(0)
     for w in (1, 4, 8, 16):
         _, l = rate(148, 0, 128, 0, w, 4000, 0)
         _, st = rate(148, 0, 128, 0, w, 4000, 1)

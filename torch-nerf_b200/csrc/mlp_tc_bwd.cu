@@ -27,12 +27,12 @@ using namespace tc;
 // ================================================================================================
 // 1. dgrad chain
 // ================================================================================================
-constexpr int kDgStages = 9;
-constexpr int kDgStageBytes = kChunkBytes;  // 128 input features x 64 output features
+constexpr int kDgStages = 5;
+constexpr int kDgStageBytes = 2 * kChunkBytes;  // two chunks (128 input features x 64 output features each) per barrier
 constexpr int kDgThreads = 320;
 constexpr int kDgEpiThreads = 256;
-constexpr int kDgSmA = 0;      // staging of the bf16 gradient blocks for the bulk stores (the MMA A operand lives in TMEM)
-constexpr int kDgSmW = 65536;
+constexpr int kDgSmA = 0;      // 8 warps x 4 KB staging of the bf16 gradient blocks for the bulk stores (the MMA A operand lives in TMEM)
+constexpr int kDgSmW = 32768;
 // tensor memory map (columns): fp32 accumulator [0,256) (two N-halves), A operand buffers [256,384) and [384,512)
 constexpr uint32_t kDgTmA = 256;
 constexpr int kDgSmC = kDgSmW + kDgStages * kDgStageBytes;  // w8row0 (256) | wout (384)
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], 128);
+    for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], kDgEpiThreads);
     mbar_init(&acc_full[0], 1);
     mbar_init(&acc_full[1], 1);
     fence_barrier_init();
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
       uint32_t g = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint8_t* src = a.packed + kPackedBwdOff;
-        for (int c = 0; c < kBwdChunks; ++c) {
+        for (int c = 0; c < kBwdChunks / 2; ++c) {  // every (layer, N-half) has an even number of chunks
           const uint32_t s = g % kDgStages, ph = (g / kDgStages) & 1;
           mbar_wait(&empty[s], ph ^ 1);
           if (leader) {
@@ -131,75 +131,46 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
       }
     }
   } else if (warp == 1) {
-    // MMA issuer: the whole warp runs the loop in lock step, one elected lane issues; a step's barriers are polled
-    // while the previous step's MMAs execute (see mlp_tc_fwd.cu)
+    // the whole warp runs the issue loop in lock step; one elected lane issues (keeps descriptors in uniform registers)
     {
       const bool leader = elect_one();
+      uint32_t g = 0;
+      uint32_t a_cnt[4] = {0, 0, 0, 0};
       constexpr uint32_t idesc = make_idesc_bf16(128, false, false);
       const uint32_t sW_u = smem_u32(sW);
-      struct Step {
-        int64_t tile;
-        int j, nh, kb;
-        uint32_t g, tile_iter;
-      };
-      auto advance = [&](Step& st) {
-        ++st.g;
-        if (++st.kb == bwd_nk(st.j)) {
-          st.kb = 0;
-          if (++st.nh == 2) {
-            st.nh = 0;
-            if (++st.j == kNumBwdLayers) {
-              st.j = 0;
-              st.tile += gridDim.x;
-              ++st.tile_iter;
-            }
-          }
-        }
-      };
-      auto first_of_tile = [](const Step& st) { return st.j == 0 && st.nh == 0 && st.kb == 0; };
-      auto wait_for = [&](const Step& st) {
-        if (st.nh == 0) {
-          if (st.kb == 0) {
-            // N-half 0 overwrites accumulator columns [0,128): both warp groups must have drained them, which each
-            // signals through its first gradient block (j == 0: the G9 blocks, written after the previous tile).
-            // a_ready[0], [1] complete 9 times per tile (input stage + layers 0..7), layer j consumes round j.
-            const uint32_t par = (st.tile_iter + (uint32_t)st.j) & 1;
-            mbar_wait(&a_ready[0], par);
-            mbar_wait(&a_ready[1], par);
-          } else if (st.kb >= 2) {
-            // a_ready[2], [3] complete 8 times per tile (layers 0..7), layer j >= 1 consumes round j - 1
-            mbar_wait(&a_ready[st.kb], (uint32_t)(st.j - 1) & 1);
-          }
-        }
-        mbar_wait(&full[st.g % kDgStages], (st.g / kDgStages) & 1);
-        tc_fence_after();
-      };
-      auto issue = [&](const Step& st, int half) {
-        const uint32_t acc = tmem_base + (uint32_t)st.nh * 128u;
-        const uint32_t a_tm = tmem_base + kDgTmA + (uint32_t)(st.j & 1) * 128u + (uint32_t)st.kb * 32u;
-        const uint64_t db = desc_kmajor(sW_u + (st.g % kDgStages) * kDgStageBytes);
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int j = 0; j < kNumBwdLayers; ++j) {
+          const int nk = bwd_nk(j);
+          const uint32_t a_tm = tmem_base + kDgTmA + (uint32_t)(j & 1) * 128u;  // this layer's A operand (G) in TMEM
+          // N-half 0 overwrites accumulator columns [0,128): both warp groups must have drained them, which they
+          // signal through the first gradient block pair (for j == 0: the G9 blocks, written after the previous tile)
+          mbar_wait(&a_ready[0], a_cnt[0] & 1);
+          ++a_cnt[0];
+          for (int nh = 0; nh < 2; ++nh) {
+            const uint32_t acc = tmem_base + (uint32_t)nh * 128u;
+#pragma unroll 1
+            for (int kb = 0; kb < nk; ++kb) {
+              if (nh == 0 && kb == 2) {
+                mbar_wait(&a_ready[1], a_cnt[1] & 1);
+                ++a_cnt[1];
+              }
+              const uint32_t s = g % kDgStages, ph = (g / kDgStages) & 1;
+              if ((kb & 1) == 0) mbar_wait(&full[s], ph);
+              tc_fence_after();
+              if (leader) {
+                const uint64_t db = desc_kmajor(sW_u + s * kDgStageBytes + (kb & 1) * kChunkBytes);
 #pragma unroll
-        for (int k = 2 * half; k < 2 * half + 2; ++k)
-          umma_bf16_ts(acc, a_tm + (uint32_t)k * 8u, db + 2 * k, idesc, (st.kb > 0 || k > 0) ? 1u : 0u);
-      };
-      Step cur{(int64_t)blockIdx.x, 0, 0, 0, 0u, 0u};
-      if (cur.tile < ntiles) wait_for(cur);
-      while (cur.tile < ntiles) {
-        Step nxt = cur;
-        advance(nxt);
-        const bool nxt_valid = nxt.tile < ntiles;
-        if (leader) issue(cur, 0);
-        __syncwarp();
-        // look ahead -- except across a tile boundary: the next tile's G9 blocks depend on this step's commit
-        if (nxt_valid && !first_of_tile(nxt)) wait_for(nxt);
-        if (leader) {
-          issue(cur, 1);
-          umma_commit(&empty[cur.g % kDgStages]);
-          if (cur.kb == bwd_nk(cur.j) - 1) umma_commit(&acc_full[cur.nh]);
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16_ts(acc, a_tm + (uint32_t)(kb * 32 + k * 8), db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                if (kb & 1) umma_commit(&empty[s]);
+              }
+              __syncwarp();
+              if (kb & 1) ++g;
+            }
+            if (leader) umma_commit(&acc_full[nh]);
+            __syncwarp();
+          }
         }
-        __syncwarp();
-        if (nxt_valid && first_of_tile(nxt)) wait_for(nxt);
-        cur = nxt;
       }
     }
   } else {
@@ -208,7 +179,8 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t accn[2] = {0, 0};
-    uint8_t* a_row = sA + row * 128;
+    uint8_t* st_slot = sA + (warp - 2) * 4096;  // this warp's 32 rows x 128 B staging slice
+    uint8_t* a_row = st_slot + lane * 128;
     float4* ghead_out = reinterpret_cast<float4*>(a.scratch + scratch_ghead_offset(a.m));
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t grow = tile * kTileM + row;
@@ -228,7 +200,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
       if (half == 0) ghead_out[tile * kTileM + row] = make_float4(gz0, gz1, gz2, gsp);
       // ---- G9 = (gz . W_out) masked by h9 > 0; this half owns columns [64*half, 64*half + 64) = block `half`
       {
-        if (lane == 0) bulk_wait_read<1>();
+        if (lane == 0) bulk_wait_read<0>();  // the previous bulk store out of this warp's staging slice has been read
         __syncwarp();
         uint32_t w[32];
 #pragma unroll
@@ -246,17 +218,17 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
           pack_words(f, w + 16 * gi);
         }
         tmem_st32(lane_addr + kDgTmA + half * 32, w);  // layer 0 reads A buffer 0
-        store_words(w, a_row + half * kBlockBytes, row, 0);
-        store_words(w + 16, a_row + half * kBlockBytes, row, 4);
+        store_words(w, a_row, row, 0);
+        store_words(w + 16, a_row, row, 4);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          bulk_s2g(g_tile + (size_t)(kGradG9 + half) * kBlockBytes + q * 4096, sA + half * kBlockBytes + q * 4096, 4096);
+          bulk_s2g(g_tile + (size_t)(kGradG9 + half) * kBlockBytes + q * 4096, st_slot, 4096);
           bulk_commit();
         }
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&a_ready[half]);
+        mbar_arrive(&a_ready[0]);  // block pair {0, 1}
       }
       for (int j = 0; j < kNumBwdLayers; ++j) {
         const uint32_t taddr = lane_addr;
@@ -276,15 +248,10 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
             m0 = __ldg(mask_tile + (slot * 8 + 2 * kb) * kTileM + row);
             m1 = __ldg(mask_tile + (slot * 8 + 2 * kb + 1) * kTileM + row);
           }
-          if (lane == 0) {
-            // the bulk store that last read this warp's slice of block kb must be done: it is the newest group only
-            // for (j == 0, t == 0), where it is the G9 store of this tile
-            if (j == 0 && t == 0) bulk_wait_read<0>();
-            else bulk_wait_read<1>();
-          }
+          if (lane == 0) bulk_wait_read<0>();
           __syncwarp();
           tmem_ld_wait();
-          uint8_t* blk_row = a_row + kb * kBlockBytes;
+          uint8_t* blk_row = a_row;
           float f[32];
           uint32_t w[32];
           masked_group(v0, m0, gsp, j == 1 ? sW8 + kb * 64 : nullptr, f);
@@ -297,13 +264,13 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            bulk_s2g(g_tile + (size_t)(2 + 4 * j + kb) * kBlockBytes + q * 4096, sA + kb * kBlockBytes + q * 4096, 4096);
+            bulk_s2g(g_tile + (size_t)(2 + 4 * j + kb) * kBlockBytes + q * 4096, st_slot, 4096);
             bulk_commit();
           }
           if (j < kNumBwdLayers - 1) {
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&a_ready[kb]);
+            mbar_arrive(&a_ready[t]);  // block pair {2t, 2t+1}
           } else {
             tc_fence_before();
           }

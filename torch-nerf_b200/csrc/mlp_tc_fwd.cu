@@ -1,7 +1,7 @@
 // K4+K5 on the sm_100a tensor cores: the NeRF MLP forward (network/nerf.py:65-121) as a chain of tcgen05 BF16 MMAs
 // with fp32 accumulation in TMEM; positional encoding (signal_encoder/positional_encoder.py:49-104, as applied by
 // scene/primitives/cube.py:62-69) is computed in-kernel as the first layer's operand; weights are streamed from L2
-// by the TMA engine (cp.async.bulk + mbarrier) through a 7-stage ring of 16 KB chunks (128 outputs x 64 inputs).
+// by the TMA engine (cp.async.bulk + mbarrier) through a 4-stage ring of 32 KB stages (two chunks of 128 outputs x 64 inputs).
 //
 // One CTA per SM, 128 sample rows per tile.  Activations live in TENSOR MEMORY between layers:
 //
@@ -36,14 +36,15 @@
 namespace nerf {
 using namespace tc;
 
-constexpr int kStages = 7;
-constexpr int kStageBytes = kChunkBytes;  // 128 output rows x 64 K-columns
+constexpr int kStages = 4;
+constexpr int kStageBytes = 2 * kChunkBytes;  // two chunks (128 output rows x 64 K-columns each) per barrier: every
+                                              // mbarrier probe costs the issuing thread ~125 cycles of dead tensor time
 constexpr int kFwdThreads = 320;
 constexpr int kEpiThreads = 256;
 // shared memory map (bytes from the 1024-aligned base)
-constexpr int kSmStage = 0;                     // 4 blocks x 16 KB: staging of bf16 activations for the cache (training)
-constexpr int kSmIn = 65536;                    // pe block 16 KB | de block 16 KB (A operands of the SS-form chunks)
-constexpr int kSmW = 98304;                     // weight ring
+constexpr int kSmStage = 0;                     // 8 warps x 4 KB: staging of bf16 activations for the cache (training)
+constexpr int kSmIn = 32768;                    // pe block 16 KB | de block 16 KB (A operands of the SS-form chunks)
+constexpr int kSmW = 65536;                     // weight ring
 constexpr int kSmC = kSmW + kStages * kStageBytes;
 constexpr int kSmX = kSmC + kCFloats * 4;       // 128 x 4 floats: partial sigma / rgb exchange between warp groups
 constexpr int kSmBar = kSmX + 128 * 16;
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmBar);
   uint64_t* full = bars;                   // [kStages]
   uint64_t* empty = bars + kStages;        // [kStages]
-  uint64_t* a_ready = bars + 2 * kStages;  // [4]   one completion per producing layer
+  uint64_t* a_ready = bars + 2 * kStages;  // [2 used] k-block pairs {0,1} and {2,3}: one completion per producing layer
   uint64_t* in_ready = a_ready + 4;        // [1]   one completion per tile
   uint64_t* acc_full = in_ready + 1;       // [2 N-halves of the accumulator]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], 128);
+    for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], kEpiThreads);
     mbar_init(in_ready, kEpiThreads);
     mbar_init(&acc_full[0], 1);
     mbar_init(&acc_full[1], 1);
@@ -186,117 +187,104 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
       uint32_t g = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint8_t* src = a.packed + kPackedFwdOff;
-        for (int c = 0; c < kFwdChunks; ++c) {
-          const uint32_t s = g % kStages, ph = (g / kStages) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
-          if (leader) {
-            mbar_arrive_expect_tx(&full[s], kStageBytes);
-            bulk_g2s(sW + s * kStageBytes, src, kStageBytes, &full[s]);
+        for (int l = 0; l < kNumFwdLayers; ++l) {
+          for (int nh = 0; nh < fwd_nh(l); ++nh) {
+            for (int c0 = 0; c0 < fwd_nk(l); c0 += 2) {
+              const uint32_t bytes = (uint32_t)min(2, fwd_nk(l) - c0) * kChunkBytes;
+              const uint32_t s = g % kStages, ph = (g / kStages) & 1;
+              mbar_wait(&empty[s], ph ^ 1);
+              if (leader) {
+                mbar_arrive_expect_tx(&full[s], bytes);
+                bulk_g2s(sW + s * kStageBytes, src, bytes, &full[s]);
+              }
+              __syncwarp();
+              src += bytes;
+              ++g;
+            }
           }
-          __syncwarp();
-          src += kStageBytes;
-          ++g;
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    // The whole warp runs this loop in lock step (waits included); one elected lane issues.  The schedule is a flat
-    // sequence of steps (tile, layer l, N-half nh, k-chunk kb).  A step's barriers are polled while the previous
-    // step's MMAs are still executing (issue first half -> poll next step's barriers -> issue second half -> commit):
-    // an mbarrier probe costs ~150 cycles even when the phase is already complete and the MMA queue is shallow, so
-    // polling between steps would starve the tensor pipe on every chunk.
+    // The whole warp runs this loop in lock step (waits included); one elected lane issues.
     {
       const bool leader = elect_one();
+      uint32_t g = 0, a_cnt = 0, in_cnt = 0;
       constexpr uint32_t idesc = make_idesc_bf16(128, false, false);
       const uint32_t sIn_u = smem_u32(sIn), sW_u = smem_u32(sW);
-      struct Step {
-        int64_t tile;
-        int l, nh, kb;
-        uint32_t g, tile_iter;
-      };
-      auto advance = [&](Step& st) {
-        ++st.g;
-        if (++st.kb == fwd_nk(st.l)) {
-          st.kb = 0;
-          if (++st.nh == fwd_nh(st.l)) {
-            st.nh = 0;
-            if (++st.l == kNumFwdLayers) {
-              st.l = 0;
-              st.tile += gridDim.x;
-              ++st.tile_iter;
-            }
-          }
-        }
-      };
-      auto first_of_tile = [](const Step& st) { return st.l == 0 && st.nh == 0 && st.kb == 0; };
-      // k-block of the TMEM A buffer this step reads, or -1 when its A operand is one of the shared-memory blocks
-      auto a_block = [](const Step& st) {
-        if (st.l == 0 || (st.l == 5 && st.kb == 0) || (st.l == 9 && st.kb == 4)) return -1;
-        return st.l == 5 ? st.kb - 1 : st.kb;
-      };
-      auto wait_for = [&](const Step& st) {
-        if (first_of_tile(st)) {
-          // encoded inputs ready; every epilogue warp has also left the previous tile (accumulator drained)
-          mbar_wait(in_ready, st.tile_iter & 1);
-        }
-        if (st.l >= 1 && st.nh == 0) {
-          // a_ready[b] completes once per producing layer 0..8 (9 per tile); layer l consumes round l - 1
-          const uint32_t a_par = (st.tile_iter + (uint32_t)(st.l - 1)) & 1;
-          if (st.kb == 0) {
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // the encoded inputs are ready; all epilogue warps have also left the previous tile (accumulator drained)
+        mbar_wait(in_ready, in_cnt & 1);
+        ++in_cnt;
+        for (int l = 0; l < kNumFwdLayers; ++l) {
+          const int nk = fwd_nk(l);
+          const uint32_t a_tm = tmem_base + kTmA + (uint32_t)(l & 1) * 128u;  // this layer's A operand in TMEM
+          const bool stamp = a.prof != nullptr && blockIdx.x == 0 && (int)in_cnt <= a.prof_tiles;
+          if (stamp && leader) a.prof[(((int)in_cnt - 1) * kNumFwdLayers + l) * 8 + 0] = clock64();
+          long long wait_a = 0, wait_w = 0;
+          // a_ready[p] (k-block pair p) completes once per producing layer 0..8; layer l >= 1 consumes round (l - 1)
+          const uint32_t a_par = (a_cnt + (uint32_t)(l - 1)) & 1;
+          if (l >= 1) {
             // N-half 0 overwrites accumulator columns [0,128): both warp groups must have drained them
+            const long long w0 = stamp ? clock64() : 0;
             mbar_wait(&a_ready[0], a_par);
-            mbar_wait(&a_ready[1], a_par);
+            if (stamp) wait_a += clock64() - w0;
           }
-          const int ab = a_block(st);
-          if (ab >= 2) mbar_wait(&a_ready[ab], a_par);
-        }
-        mbar_wait(&full[st.g % kStages], (st.g / kStages) & 1);
-        tc_fence_after();
-      };
-      auto issue = [&](const Step& st, int half) {
-        const uint32_t acc = tmem_base + kTmAcc + (uint32_t)st.nh * 128u;
-        const uint64_t db = desc_kmajor(sW_u + (st.g % kStages) * kStageBytes);
-        const int ab = a_block(st);
-        if (ab >= 0) {
-          const uint32_t a_tm = tmem_base + kTmA + (uint32_t)(st.l & 1) * 128u + (uint32_t)ab * 32u;
+          for (int nh = 0; nh < fwd_nh(l); ++nh) {
+            const uint32_t acc = tmem_base + kTmAcc + (uint32_t)nh * 128u;
+            for (int kb = 0; kb < nk; ++kb) {
+              int ab = -1;             // A k-block in TMEM, or -1 for the shared-memory blocks
+              uint32_t a_smem = 0;
+              int nsteps = 4;
+              if (l == 0 || (l == 5 && kb == 0)) {
+                a_smem = sIn_u;                      // encoded position
+              } else if (l == 9 && kb == 4) {
+                a_smem = sIn_u + kBlockBytes;        // encoded view direction (K = 32)
+                nsteps = 2;
+              } else {
+                ab = (l == 5) ? kb - 1 : kb;
+                if (nh == 0 && ab == 2) {
+                  const long long w0 = stamp ? clock64() : 0;
+                  mbar_wait(&a_ready[1], a_par);
+                  if (stamp) wait_a += clock64() - w0;
+                }
+              }
+              const uint32_t s = g % kStages, ph = (g / kStages) & 1;
+              if ((kb & 1) == 0) {  // first chunk of a weight stage
+                const long long w1 = stamp ? clock64() : 0;
+                mbar_wait(&full[s], ph);
+                if (stamp) wait_w += clock64() - w1;
+              }
+              tc_fence_after();
+              const bool stage_done = (kb & 1) || kb == nk - 1;
+              if (leader) {
+                const uint64_t db = desc_kmajor(sW_u + s * kStageBytes + (kb & 1) * kChunkBytes);
+                if (ab >= 0) {
 #pragma unroll
-          for (int k = 2 * half; k < 2 * half + 2; ++k)
-            umma_bf16_ts(acc, a_tm + (uint32_t)k * 8u, db + 2 * k, idesc, (st.kb > 0 || k > 0) ? 1u : 0u);
-        } else {
-          const bool view = (st.l == 9);  // encoded view direction: K = 32 (two MMAs), else encoded position (four)
-          const uint64_t da = desc_kmajor(view ? sIn_u + kBlockBytes : sIn_u);
-          if (view) {
-            umma_bf16(acc, da + 2 * half, db + 2 * half, idesc, 1u);
-          } else {
-#pragma unroll
-            for (int k = 2 * half; k < 2 * half + 2; ++k)
-              umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (st.kb > 0 || k > 0) ? 1u : 0u);
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16_ts(acc, a_tm + (uint32_t)(ab * 32 + k * 8), db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                } else {
+                  const uint64_t da = desc_kmajor(a_smem);
+#pragma unroll 4
+                  for (int k = 0; k < nsteps; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                }
+                if (stage_done) umma_commit(&empty[s]);
+              }
+              __syncwarp();
+              if (stage_done) ++g;
+            }
+            if (leader) umma_commit(&acc_full[nh]);
+            __syncwarp();
+          }
+          if (stamp && leader) {
+            unsigned long long* pr = a.prof + (((int)in_cnt - 1) * kNumFwdLayers + l) * 8;
+            pr[1] = clock64();
+            pr[4] = (unsigned long long)wait_a;
+            pr[5] = (unsigned long long)wait_w;
           }
         }
-      };
-      Step cur{(int64_t)blockIdx.x, 0, 0, 0, 0u, 0u};
-      if (cur.tile < ntiles) wait_for(cur);
-      while (cur.tile < ntiles) {
-        Step nxt = cur;
-        advance(nxt);
-        const bool nxt_valid = nxt.tile < ntiles;
-        const bool stamp = a.prof != nullptr && blockIdx.x == 0 && (int)cur.tile_iter < a.prof_tiles && leader;
-        if (stamp && cur.nh == 0 && cur.kb == 0) a.prof[(cur.tile_iter * kNumFwdLayers + cur.l) * 8 + 0] = clock64();
-        if (leader) issue(cur, 0);
-        __syncwarp();
-        // look ahead -- except across a tile boundary: in_ready of the next tile depends on this step's commit
-        if (nxt_valid && !first_of_tile(nxt)) wait_for(nxt);
-        if (leader) {
-          issue(cur, 1);
-          umma_commit(&empty[cur.g % kStages]);
-          if (cur.kb == fwd_nk(cur.l) - 1) umma_commit(&acc_full[cur.nh]);
-        }
-        __syncwarp();
-        if (stamp && cur.kb == fwd_nk(cur.l) - 1 && cur.nh == fwd_nh(cur.l) - 1)
-          a.prof[(cur.tile_iter * kNumFwdLayers + cur.l) * 8 + 1] = clock64();
-        if (nxt_valid && first_of_tile(nxt)) wait_for(nxt);
-        cur = nxt;
+        a_cnt += 9;
       }
     }
   } else {
@@ -306,7 +294,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t accn[2] = {0, 0};  // completions seen per N-half barrier
-    uint8_t* st_row = sStage + row * 128;
+    uint8_t* st_slot = sStage + (warp - 2) * 4096;  // this warp's 32 rows x 128 B staging slice
+    uint8_t* st_row = st_slot + lane * 128;
     int tile_iter = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_iter) {
       const int64_t grow = tile * kTileM + row;
@@ -337,7 +326,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
           }
         }
         if (kTrain) {
-          if (lane == 0) bulk_wait_read<1>();
+          if (lane == 0) bulk_wait_read<0>();  // the previous tile's stores (incl. the one out of the input block) are read
           __syncwarp();
         }
         if (half == 0) encode_row<10, 8>(x, y, z, sIn + row * 128, row);
@@ -372,7 +361,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
             tmem_ld32(taddr + kb * 64, v0);
             tmem_ld32(taddr + kb * 64 + 32, v1);
             if (kTrain) {
-              if (lane == 0) bulk_wait_read<1>();  // this warp's previous store out of staging block kb has been read
+              if (lane == 0) bulk_wait_read<0>();  // this warp's previous bulk store out of its staging slice has been read
               __syncwarp();
             }
             tmem_ld_wait();
@@ -397,20 +386,19 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
             pack_group(f, w + 16);
             tmem_st32(a_next + kb * 32, w);  // 64 bf16 = 32 packed columns of this row
             if (kTrain) {
-              uint8_t* blk_row = st_row + kb * kBlockBytes;
-              store_words(w, blk_row, row, 0);
-              store_words(w + 16, blk_row, row, 4);
+              store_words(w, st_row, row, 0);
+              store_words(w + 16, st_row, row, 4);
               fence_proxy_async();
               __syncwarp();
               if (lane == 0) {
                 const int blk = (l < 8 ? cache_h(l) : kCacheFeat) + kb;
-                bulk_s2g(cache_tile + (size_t)blk * kBlockBytes + q * 4096, sStage + kb * kBlockBytes + q * 4096, 4096);
+                bulk_s2g(cache_tile + (size_t)blk * kBlockBytes + q * 4096, st_slot, 4096);
                 bulk_commit();
               }
             }
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&a_ready[kb]);
+            mbar_arrive(&a_ready[t]);  // k-block pair t = {2t, 2t+1}
           }
           if (l == 7 && half == 1) sX[row * 4 + 3] = sigma_part;
           if (stamp) a.prof[((tile_iter * kNumFwdLayers + l) * 8) + 3] = clock64();
@@ -424,7 +412,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
           tmem_ld32(taddr + half * 64, v0);
           tmem_ld32(taddr + half * 64 + 32, v1);
           if (kTrain) {
-            if (lane == 0) bulk_wait_read<1>();
+            if (lane == 0) bulk_wait_read<0>();
             __syncwarp();
           }
           tmem_ld_wait();
@@ -451,14 +439,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
           if (kTrain) {
             mask_tile[(64 + 2 * half + 1) * kTileM + row] = neg;
             pack_group(f, w + 16);
-            uint8_t* blk_row = st_row + half * kBlockBytes;
-            store_words(w, blk_row, row, 0);
-            store_words(w + 16, blk_row, row, 4);
+            store_words(w, st_row, row, 0);
+            store_words(w + 16, st_row, row, 4);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-              bulk_s2g(cache_tile + (size_t)(kCacheH9 + half) * kBlockBytes + q * 4096,
-                       sStage + half * kBlockBytes + q * 4096, 4096);
+              bulk_s2g(cache_tile + (size_t)(kCacheH9 + half) * kBlockBytes + q * 4096, st_slot, 4096);
               bulk_commit();
             }
           }

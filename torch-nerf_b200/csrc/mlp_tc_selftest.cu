@@ -126,35 +126,48 @@ __global__ void __launch_bounds__(640, 1) mma_rate_kernel(int iters, int n, int 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ uint64_t bar;
+  __shared__ uint64_t bar2[2];  // [0]: target of per-group commits, [1]: a completed barrier to probe
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
   fence_proxy_async();
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
+    mbar_init(&bar2[0], 1);
+    mbar_init(&bar2[1], 1);
     fence_barrier_init();
+    mbar_arrive(&bar2[1]);  // phase 0 of bar2[1] is complete: waiting on parity 0 returns at once
   }
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  if (threadIdx.x == 0 && iters > 0) {
+  if (warp == 0 && iters > 0) {
+    // issue pattern of the chain kernels: the whole warp runs the loop, one elected lane issues
+    const bool leader = elect_one();
     const uint32_t idesc = make_idesc_bf16((uint32_t)n, false, false);
     const uint64_t da = desc_kmajor(smem_u32(smem));
     const uint64_t db = desc_kmajor(smem_u32(smem) + 16384);
     const long long t0 = clock64();
+    const int m = mode & 1;
     for (int it = 0; it < iters; ++it) {
+      if (mode & 4) mbar_wait(&bar2[1], 0);  // probe an already-completed barrier before every group
+      if (leader) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (mode == 0) umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, 1u);
-        else umma_bf16_ts(tmem_base, tmem_base + 256 + 8 * k, db + 2 * k, idesc, 1u);
+        for (int k = 0; k < 4; ++k) {
+          if (m == 0) umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, 1u);
+          else umma_bf16_ts(tmem_base, tmem_base + 256 + 8 * k, db + 2 * k, idesc, 1u);
+        }
+        if (mode & 2) umma_commit(&bar2[0]);  // commit after every group (nobody waits on it)
       }
+      if (mode & 8) __syncwarp();
     }
-    umma_commit(&bar);
+    if (leader) umma_commit(&bar);
+    __syncwarp();
     mbar_wait(&bar, 0);
     const long long t1 = clock64();
-    out[blockIdx.x] = (unsigned long long)(t1 - t0);
+    if (lane == 0) out[blockIdx.x] = (unsigned long long)(t1 - t0);
   }
   if (warp >= 4 && warp < 4 + bg_warps) {
     // background tensor-memory traffic on columns [384,512) (not touched by the MMAs)
@@ -202,7 +215,7 @@ int nerf_selftest_umma(const uint16_t* a_dev, const uint16_t* b_dev, float* d_de
 
 int nerf_selftest_mma_rate(int blocks, int iters, int n, int mode, int bg_warps, int bg_iters, int bg_store,
                            unsigned long long* cycles_dev, nerf_stream_t stream) {
-  NERF_CHECK_ARG(cycles_dev && blocks > 0 && iters >= 0 && n >= 16 && n <= 256 && n % 16 == 0 && (mode == 0 || mode == 1) &&
+  NERF_CHECK_ARG(cycles_dev && blocks > 0 && iters >= 0 && n >= 16 && n <= 256 && n % 16 == 0 && mode >= 0 && mode < 16 &&
                      bg_warps >= 0 && bg_warps <= 16 && bg_iters >= 0,
                  "nerf_selftest_mma_rate: bad arguments");
   const size_t smem = 16384 + 32768 + 1024;
