@@ -235,12 +235,16 @@ def run_b200(args):
     e2e_value = rays_total / (ms_e2e * 1e-3)
     pk = peaks()
 
-    # ---- roofline of the dominant kernel: the tensor-core forward chain on the fine pass's rows
+    # ---- rooflines, measured live with CUDA events on the launching stream (kernels timed alone -> burst peaks):
+    #   roofline       = the step's dominant kernel, mlp_wgrad_kernel on the fine pass's rows (HBM-bound by construction)
+    #   roofline_mlp   = the tensor-core forward chain on the same rows (tensor-bound)
     roof = None
+    roof_mlp = None
     render = None
     if rank == 0:
         if True:
             lib = tn._lib.load()
+            P = tn._lib.ptr
             m = n_rays * (SC + SF)
             ray_o = torch.randn(n_rays, 3, device=dev)
             ray_d = torch.randn(n_rays, 3, device=dev)
@@ -248,26 +252,53 @@ def run_b200(args):
             sig = torch.empty(m, device=dev)
             rgb = torch.empty(m, 3, device=dev)
             packed = fine.packed_weights()
-            P = tn._lib.ptr
 
-            def k():
+            def timed_kernel(fn, reps=10):
+                for _ in range(3):
+                    fn()
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                ev0.record()
+                for _ in range(reps):
+                    fn()
+                ev1.record()
+                torch.cuda.synchronize()
+                return ev0.elapsed_time(ev1) * 1e-3 / reps
+
+            def k_fwd():
                 tn._lib.check(lib.nerf_mlp_bf16_forward(P(packed, torch.uint8), None, None, P(ray_o), P(ray_d), P(t), SC + SF, m,
                                                         P(sig), P(rgb), None, tn._lib.stream()), "fwd")
-            for _ in range(3):
-                k()
-            reps = 10
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            ev0.record()
-            for _ in range(reps):
-                k()
-            ev1.record()
-            torch.cuda.synchronize()
-            sec = ev0.elapsed_time(ev1) * 1e-3 / reps
+            sec = timed_kernel(k_fwd)
             ach = m * FLOP_FWD_PER_EVAL / sec / 1e12
-            roof = {"bound": "tensor", "kernel": "mlp_fwd_kernel (tcgen05 forward chain, 786432 rows)", "achieved": ach,
-                    "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "traffic": None,
-                    "peak_source": pk["src"] + " (burst: kernel timed alone)", "launch_ms": sec * 1e3}
+            roof_mlp = {"bound": "tensor", "kernel": "mlp_fwd_kernel (tcgen05 forward chain, 786432 rows, inference form)",
+                        "achieved": ach, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "traffic": None,
+                        "peak_source": pk["src"] + " (burst: kernel timed alone)", "launch_ms": sec * 1e3}
+            # wgrad alone: fill cache + scratch with one full forward/backward, then re-run only the wgrad phase
+            cache = torch.empty(lib.nerf_mlp_bf16_cache_bytes(m), dtype=torch.uint8, device=dev)
+            scratch = torch.empty(lib.nerf_mlp_bf16_bwd_scratch_bytes(m), dtype=torch.uint8, device=dev)
+            g_s = torch.randn(m, device=dev) * 1e-3
+            g_c = torch.randn(m, 3, device=dev) * 1e-3
+            grads = [torch.empty_like(p) for p in fine.ordered_parameters()]
+            garr = tn._lib.pointer_array(grads)
+            tn._lib.check(lib.nerf_mlp_bf16_forward(P(packed, torch.uint8), None, None, P(ray_o), P(ray_d), P(t), SC + SF, m,
+                                                    P(sig), P(rgb), P(cache, torch.uint8), tn._lib.stream()), "fwd-train")
+
+            def k_bwd():
+                tn._lib.check(lib.nerf_mlp_bf16_backward(P(packed, torch.uint8), P(cache, torch.uint8), P(rgb), m, P(g_s), P(g_c),
+                                                         garr, P(scratch, torch.uint8), tn._lib.stream()), "bwd")
+            k_bwd()
+            lib.nerf_debug_set_bwd_phases(4)
+            sec_w = timed_kernel(k_bwd)
+            lib.nerf_debug_set_bwd_phases(7)
+            tiles = (m + 127) // 128
+            alg_bytes = tiles * (83 * 16384 + 2 * 128 * 16)  # 83 blocks of 16 KB (G and X tile images) + head gradients per tile
+            ach_w = alg_bytes / sec_w / 1e9
+            roof = {"bound": "hbm", "kernel": "mlp_wgrad_kernel (split-K tcgen05 weight gradients, 786432 rows)",
+                    "achieved": ach_w, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_w / pk["hbm_gbs"],
+                    "traffic": 8.356e9,  # dram__bytes_read + write of one launch, ncu --set full (profiles/r01_ncu_wgrad.txt)
+                    "algorithmic_bytes": alg_bytes, "peak_source": pk["src"] + " (burst: kernel timed alone)",
+                    "launch_ms": sec_w * 1e3}
+            del cache, scratch
         # ---- full 800x800 frame (configs[2])
         cam = cams[0]
         for _ in range(2):
@@ -306,7 +337,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks,
             "step_tensor_frac_sustained": step_flop / (ms_dev / args.steps * 1e-3) / 1e12 / pk["tf_sustained"],
-            "roofline": roof, "cpu_baseline": cpu, "render": render,
+            "roofline": roof, "roofline_mlp": roof_mlp, "cpu_baseline": cpu, "render": render,
             "loss_last": [float(x) for x in losses_host[total_steps - 1]],
         }
         print(json.dumps(line))

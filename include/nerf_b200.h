@@ -190,6 +190,10 @@ int nerf_selftest_umma(const uint16_t* a_dev, const uint16_t* b_dev, float* d_de
  * for activations, 5 waiting for weights.  Pass NULL to switch it off. */
 int nerf_debug_set_profile_buffer(unsigned long long* buf_dev, int tiles);
 
+/* profiling aid: selects which phases nerf_mlp_bf16_backward runs (bit 0 zero gradients, bit 1 dgrad chain, bit 2 wgrad;
+ * default 7).  Lets bench.py time the HBM-bound wgrad kernel alone on a scratch buffer a full backward has filled. */
+int nerf_debug_set_bwd_phases(int mask);
+
 /* micro-benchmark: `blocks` CTAs each issue `iters` x 4 tcgen05.mma (M=128, N=n, K=16) -- mode bit 0: A operand from TMEM instead of
  * shared memory; bit 1: tcgen05.commit after every group of 4; bit 2: probe a completed mbarrier before every group -- while `bg_warps` extra warps each perform `bg_iters` tcgen05.ld
  * (bg_store = 0) or tcgen05.st (1) of 32 lanes x 32 columns.  cycles_dev[block] = SM cycles of the MMA thread,

@@ -196,3 +196,65 @@ def test_engine_bf16_grads_match_fp32_at_scale(tn, n):
     # coarse weights, so its gradients agree a little less
     bad = [r for r in report if r[1] < (0.98 if r[0].startswith("c/") else 0.95) or abs(r[2] - 1) > 0.15]
     assert not bad, "\n".join(f"{k}: cos {c:.4f} norm ratio {r:.3f}" for k, c, r in report)
+
+
+def test_config_c1_full_frame_100x100_fp32_vs_oracle(tn):
+    """BASELINE.json configs[0]: 100x100 Blender-shaped view, random-init networks, 64 + 128 samples, rendered whole
+    (render.py:58-107) in fp32-validation mode and compared with the CPU oracle on identical uniforms: <= 1e-3."""
+    from torch_nerf_b200.engine import HotPathEngine
+
+    h = w = 100
+    n = h * w
+    rng = np.random.default_rng(100)
+    focal = orc.blender_focal(w)
+    c2w = orc.pose_spherical(75.0, -30.0, 4.0)
+    cam = tn.PerspectiveCamera({"f_x": focal, "f_y": focal, "img_width": w, "img_height": h}, torch.from_numpy(c2w), 2.0, 6.0)
+    pc, pf = orc.init_nerf_params(seed=81), orc.init_nerf_params(seed=82)
+    coarse, fine = nets(tn, 81, 82, "fp32")
+    eng = HotPathEngine(coarse, fine, 64, 128, precision="fp32")
+    u = [rng.random((n, k), dtype=np.float32) for k in (64, 64, 128, 128)]
+    ray_o, ray_d, _ = eng.rays_from_pixels(cam, False, None, 0, n)
+    out = eng.render_rays(ray_o, ray_d, 2.0, 6.0, uniforms=tuple(cu(x) for x in u))
+    torch.cuda.synchronize()
+    o, d = orc.generate_rays(orc.screen_coords(h, w), orc.make_intrinsic(focal, focal, w, h), c2w, 2.0, h, w, False)
+    np.testing.assert_allclose(ray_d.cpu().numpy(), d, rtol=1e-6, atol=1e-7)
+    co = orc.render_pass(pc, o, d, 2.0, 6.0, 64, (u[0],), num_ray_batch=2)
+    np.testing.assert_allclose(out["rgb_coarse"].cpu().numpy(), co["rgb"], rtol=0, atol=1e-3)
+    np.testing.assert_allclose(out["weights_coarse"].cpu().numpy(), co["weights"], rtol=0, atol=1e-3)
+    # fine pass of the oracle from the GPU's coarse weights: bin decisions on identical inputs
+    fi = orc.render_pass(pf, o, d, 2.0, 6.0, (64, 128), (u[1], u[2], u[3]), weights=out["weights_coarse"].cpu().numpy().copy(),
+                         num_ray_batch=2)
+    np.testing.assert_allclose(out["t_fine"].cpu().numpy(), fi["t"], rtol=0, atol=0)
+    np.testing.assert_allclose(out["rgb_fine"].cpu().numpy(), fi["rgb"], rtol=0, atol=1e-3)
+    np.testing.assert_allclose(out["weights_fine"].cpu().numpy(), fi["weights"], rtol=0, atol=1e-3)
+
+
+@pytest.mark.parametrize("near", [0.0, 1.0])
+def test_config_c5_llff_ndc_train_step_fp32_vs_oracle(tn, near):
+    """BASELINE.json configs[4] shape: forward-facing 1008x756 camera projected to NDC (near forced to 0.0 as in
+    runner_utils.py:489-491, and the non-degenerate near = 1.0), one training iteration on 256 rays."""
+    from torch_nerf_b200.engine import HotPathEngine
+
+    h, w, focal = 756, 1008, 815.13
+    n = 256
+    rng = np.random.default_rng(int(near) + 7)
+    c2w = np.eye(4, dtype=np.float32)[:3]
+    c2w[:, 3] = [0.11, -0.05, 0.31]
+    cam = tn.PerspectiveCamera({"f_x": focal, "f_y": focal, "img_width": w, "img_height": h}, torch.from_numpy(c2w), near, 1.0)
+    pix = rng.choice(h * w, size=n, replace=False).astype(np.int64)
+    target = rng.random((n, 3), dtype=np.float32)
+    u = [rng.random((n, k), dtype=np.float32) for k in (64, 64, 128, 128)]
+    pc, pf = orc.init_nerf_params(seed=91), orc.init_nerf_params(seed=92)
+    coarse, fine = nets(tn, 91, 92, "fp32")
+    eng = HotPathEngine(coarse, fine, 64, 128, precision="fp32")
+    losses = eng.train_pixels(cam, cu(pix), cu(target), True, uniforms=tuple(cu(x) for x in u))
+    torch.cuda.synchronize()
+    o, d = orc.generate_rays(orc.screen_coords(h, w)[pix], orc.make_intrinsic(focal, focal, w, h), c2w, near, h, w, True)
+    ref = orc.train_step_grads(pc, pf, o, d, near, 1.0, 64, 128, target, *u)
+    np.testing.assert_allclose(eng.last["coarse"]["rgb"].cpu().numpy(), ref["coarse_rgb"], rtol=0, atol=1e-3)
+    np.testing.assert_allclose(eng.last["fine"]["rgb"].cpu().numpy(), ref["fine_rgb"], rtol=0, atol=1e-3)
+    np.testing.assert_allclose(losses.cpu().numpy(), [ref["coarse_loss"], ref["fine_loss"]], rtol=1e-3)
+    for tag, net in (("coarse", coarse), ("fine", fine)):
+        for k, p in net.named_parameters():
+            r = ref[f"{tag}_grads"][k]
+            np.testing.assert_allclose(p.grad.cpu().numpy(), r, rtol=5e-3, atol=5e-3 * (np.abs(r).max() + 1e-9), err_msg=f"{tag}/{k}")

@@ -64,6 +64,7 @@ _PROTOTYPES = {
     "nerf_mlp_bf16_backward": (c_int, [_P, _P, _P, c_int64, _P, _P, POINTER(_P), _P, _P]),
     "nerf_selftest_umma": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
     "nerf_debug_set_profile_buffer": (c_int, [_P, c_int]),
+    "nerf_debug_set_bwd_phases": (c_int, [c_int]),
     "nerf_selftest_mma_rate": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
 }
 

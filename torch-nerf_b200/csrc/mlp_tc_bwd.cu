@@ -617,10 +617,16 @@ __global__ void zero_grads_kernel(ParamPtrs g) {
 }
 
 static bool g_wunits_ready = false;
+static int g_bwd_phase_mask = 7;  // bit 0: zero the gradients, bit 1: dgrad chain, bit 2: wgrad (profiling aid)
 
 }  // namespace nerf
 
 using namespace nerf;
+
+extern "C" int nerf_debug_set_bwd_phases(int mask) {
+  g_bwd_phase_mask = mask;
+  return NERF_OK;
+}
 
 extern "C" int nerf_mlp_bf16_backward(const void* packed_dev, const void* cache_dev, const float* rgb_dev, int64_t m,
                                       const float* g_sigma_dev, const float* g_rgb_dev, float* const* grads,
@@ -646,11 +652,13 @@ extern "C" int nerf_mlp_bf16_backward(const void* packed_dev, const void* cache_
     NERF_CHECK_ARG(grads[i] != nullptr, "nerf_mlp_bf16_backward: null gradient pointer");
     gp.p[i] = grads[i];
   }
-  zero_grads_kernel<<<dim3(32, 22), 256, 0, st>>>(gp);
-  NERF_LAUNCH_CHECK();
+  if (g_bwd_phase_mask & 1) {
+    zero_grads_kernel<<<dim3(32, 22), 256, 0, st>>>(gp);
+    NERF_LAUNCH_CHECK();
+  }
   const int64_t ntiles = num_tiles(m);
   const int sms = sm_count();
-  {
+  if (g_bwd_phase_mask & 2) {
     DgradArgs a;
     a.packed = reinterpret_cast<const uint8_t*>(packed_dev);
     a.cache = reinterpret_cast<const uint8_t*>(cache_dev);
@@ -661,7 +669,7 @@ extern "C" int nerf_mlp_bf16_backward(const void* packed_dev, const void* cache_
     mlp_dgrad_kernel<<<grid, kDgThreads, kDgSmemBytes, st>>>(a);
     NERF_LAUNCH_CHECK();
   }
-  {
+  if (g_bwd_phase_mask & 4) {
     WgradArgs a;
     a.cache = reinterpret_cast<const uint8_t*>(cache_dev);
     a.scratch = reinterpret_cast<const uint8_t*>(scratch_dev);
