@@ -186,7 +186,11 @@ class HotPathEngine:
             uc = self._uniforms(n, None if uniforms is None else uniforms[:1], fine=False)
             co = self._pass(0, "c", ray_o, ray_d, n, float(near), float(far), None, uc, train=False)
             uf = self._uniforms(n, None if uniforms is None else uniforms[1:], fine=True)
-            fi = self._pass(1, "f", ray_o, ray_d, n, float(near), float(far), co["w"], uf, train=False)
+            # the fine pass perturbs ITS copy of the coarse weights in place (utils.py:31); the returned coarse
+            # weights stay as rendered
+            w_pdf = self._get("w_pdf", (n, self.sc))
+            w_pdf.copy_(co["w"])
+            fi = self._pass(1, "f", ray_o, ray_d, n, float(near), float(far), w_pdf, uf, train=False)
         return {"rgb_coarse": co["rgb"], "weights_coarse": co["w"], "rgb_fine": fi["rgb"], "weights_fine": fi["w"],
                 "t_fine": fi["t"]}
 
