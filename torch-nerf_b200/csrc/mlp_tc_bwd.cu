@@ -29,7 +29,8 @@ using namespace tc;
 // ================================================================================================
 constexpr int kDgStages = 5;
 constexpr int kDgStageBytes = 2 * kChunkBytes;  // two chunks (128 input features x 64 output features each) per barrier
-constexpr int kDgThreads = 320;
+constexpr int kDgThreads = 352;  // loader, MMA issuer A, 8 epilogue warps, MMA issuer B
+constexpr int kDgMmaWarpB = 10;
 constexpr int kDgEpiThreads = 256;
 constexpr int kDgSmA = 0;      // 8 warps x 4 KB staging of the bf16 gradient blocks for the bulk stores (the MMA A operand lives in TMEM)
 constexpr int kDgSmW = 32768;
@@ -130,46 +131,48 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
         }
       }
     }
-  } else if (warp == 1) {
-    // the whole warp runs the issue loop in lock step; one elected lane issues (keeps descriptors in uniform registers)
+  } else if (warp == 1 || warp == kDgMmaWarpB) {
+    // two MMA issuers (see mlp_tc_fwd.cu): warp 1 issues N-half 0 of every layer, warp kDgMmaWarpB N-half 1, so one
+    // warp's barrier probes overlap the other's MMAs.  Each warp runs in lock step, one elected lane issues.
     {
+      const int nh = (warp == 1) ? 0 : 1;
       const bool leader = elect_one();
-      uint32_t g = 0;
-      uint32_t a_cnt[4] = {0, 0, 0, 0};
+      uint32_t g_layer = 0, tile_iter = 0;
       constexpr uint32_t idesc = make_idesc_bf16(128, false, false);
       const uint32_t sW_u = smem_u32(sW);
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const uint32_t acc = tmem_base + (uint32_t)nh * 128u;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_iter) {
         for (int j = 0; j < kNumBwdLayers; ++j) {
           const int nk = bwd_nk(j);
+          const uint32_t stages_per_half = (uint32_t)nk / 2;
+          uint32_t g = g_layer + (nh ? stages_per_half : 0u);
+          g_layer += 2 * stages_per_half;
           const uint32_t a_tm = tmem_base + kDgTmA + (uint32_t)(j & 1) * 128u;  // this layer's A operand (G) in TMEM
-          // N-half 0 overwrites accumulator columns [0,128): both warp groups must have drained them, which they
-          // signal through the first gradient block pair (for j == 0: the G9 blocks, written after the previous tile)
-          mbar_wait(&a_ready[0], a_cnt[0] & 1);
-          ++a_cnt[0];
-          for (int nh = 0; nh < 2; ++nh) {
-            const uint32_t acc = tmem_base + (uint32_t)nh * 128u;
+          // a_ready[0] (blocks {0,1}) completes 9 times per tile (input stage + layers 0..7): layer j consumes round j.
+          // a_ready[1] (blocks {2,3}) completes 8 times per tile (layers 0..7): layer j >= 1 consumes round j - 1;
+          // every epilogue thread arrives on pair 0 before pair 1, so pair 1 complete implies pair 0 complete.
+          // N-half 0 overwrites accumulator columns [0,128) (drained before pair 0 is signalled), N-half 1 columns
+          // [128,256) (drained before pair 1 / before the next tile's G9 blocks are signalled).
+          if (nh == 0 || j == 0) mbar_wait(&a_ready[0], (tile_iter + (uint32_t)j) & 1);
+          else mbar_wait(&a_ready[1], (uint32_t)(j - 1) & 1);
 #pragma unroll 1
-            for (int kb = 0; kb < nk; ++kb) {
-              if (nh == 0 && kb == 2) {
-                mbar_wait(&a_ready[1], a_cnt[1] & 1);
-                ++a_cnt[1];
-              }
-              const uint32_t s = g % kDgStages, ph = (g / kDgStages) & 1;
-              if ((kb & 1) == 0) mbar_wait(&full[s], ph);
-              tc_fence_after();
-              if (leader) {
-                const uint64_t db = desc_kmajor(sW_u + s * kDgStageBytes + (kb & 1) * kChunkBytes);
+          for (int kb = 0; kb < nk; ++kb) {
+            if (nh == 0 && kb == 2) mbar_wait(&a_ready[1], (uint32_t)(j - 1) & 1);
+            const uint32_t s = g % kDgStages, ph = (g / kDgStages) & 1;
+            if ((kb & 1) == 0) mbar_wait(&full[s], ph);
+            tc_fence_after();
+            if (leader) {
+              const uint64_t db = desc_kmajor(sW_u + s * kDgStageBytes + (kb & 1) * kChunkBytes);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16_ts(acc, a_tm + (uint32_t)(kb * 32 + k * 8), db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                if (kb & 1) umma_commit(&empty[s]);
-              }
-              __syncwarp();
-              if (kb & 1) ++g;
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_ts(acc, a_tm + (uint32_t)(kb * 32 + k * 8), db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              if (kb & 1) umma_commit(&empty[s]);
             }
-            if (leader) umma_commit(&acc_full[nh]);
             __syncwarp();
+            if (kb & 1) ++g;
           }
+          if (leader) umma_commit(&acc_full[nh]);
+          __syncwarp();
         }
       }
     }

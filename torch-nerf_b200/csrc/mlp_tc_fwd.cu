@@ -10,7 +10,7 @@
 //                [384,512)  A operand buffer 1                                          / buffer l&1, writes (l+1)&1
 //
 //   warp 0      weight loader   1-D bulk copies of pre-swizzled bf16 weight chunks
-//   warp 1      MMA issuer      one thread issues tcgen05.mma (M=128, N=128, K=16) in the TS form: A from TMEM, B from
+//   warps 1,10  MMA issuers     one thread each issues tcgen05.mma (M=128, N=128, K=16) in the TS form: A from TMEM, B from
 //                               shared memory -- this takes the activations off the shared-memory port, which limits
 //                               the SS form to one 128x256x16 MMA per 168 cycles.  A 256-wide layer is two N-halves
 //                               committed separately: while the tensor pipe computes output columns [128,256) the
@@ -39,7 +39,8 @@ using namespace tc;
 constexpr int kStages = 4;
 constexpr int kStageBytes = 2 * kChunkBytes;  // two chunks (128 output rows x 64 K-columns each) per barrier: every
                                               // mbarrier probe costs the issuing thread ~125 cycles of dead tensor time
-constexpr int kFwdThreads = 320;
+constexpr int kFwdThreads = 352;   // loader, MMA issuer A, 8 epilogue warps, MMA issuer B
+constexpr int kMmaWarpB = 10;
 constexpr int kEpiThreads = 256;
 // shared memory map (bytes from the 1024-aligned base)
 constexpr int kSmStage = 0;                     // 8 warps x 4 KB: staging of bf16 activations for the cache (training)
@@ -205,78 +206,86 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    // The whole warp runs this loop in lock step (waits included); one elected lane issues.
+  } else if (warp == 1 || warp == kMmaWarpB) {
+    // ------------------------------------------------------------------ MMA issuers (two warps)
+    // tcgen05.mma issue is effectively synchronous (the issuing thread is held while its MMA executes) and every
+    // mbarrier probe costs ~125-150 cycles, so a single issuer leaves the tensor pipe idle during each probe.  Warp 1
+    // issues N-half 0 of every layer, warp kMmaWarpB N-half 1: while one polls its barriers the other's MMAs run.
+    // Each warp runs its loop in lock step and one elected lane issues.
     {
+      const int nh = (warp == 1) ? 0 : 1;
       const bool leader = elect_one();
-      uint32_t g = 0, a_cnt = 0, in_cnt = 0;
+      uint32_t g_layer = 0, a_cnt = 0, in_cnt = 0;
       constexpr uint32_t idesc = make_idesc_bf16(128, false, false);
       const uint32_t sIn_u = smem_u32(sIn), sW_u = smem_u32(sW);
+      const uint32_t acc = tmem_base + kTmAcc + (uint32_t)nh * 128u;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         // the encoded inputs are ready; all epilogue warps have also left the previous tile (accumulator drained)
         mbar_wait(in_ready, in_cnt & 1);
         ++in_cnt;
         for (int l = 0; l < kNumFwdLayers; ++l) {
           const int nk = fwd_nk(l);
+          const uint32_t stages_per_half = (uint32_t)(nk + 1) / 2;
+          uint32_t g = g_layer + (nh ? stages_per_half : 0u);  // this warp's first weight stage of the layer
+          g_layer += stages_per_half * (uint32_t)fwd_nh(l);
+          if (nh >= fwd_nh(l)) continue;                      // fc_9 is a single N-half
           const uint32_t a_tm = tmem_base + kTmA + (uint32_t)(l & 1) * 128u;  // this layer's A operand in TMEM
-          const bool stamp = a.prof != nullptr && blockIdx.x == 0 && (int)in_cnt <= a.prof_tiles;
+          const bool stamp = a.prof != nullptr && blockIdx.x == 0 && (int)in_cnt <= a.prof_tiles && nh == 0;
           if (stamp && leader) a.prof[(((int)in_cnt - 1) * kNumFwdLayers + l) * 8 + 0] = clock64();
           long long wait_a = 0, wait_w = 0;
-          // a_ready[p] (k-block pair p) completes once per producing layer 0..8; layer l >= 1 consumes round (l - 1)
+          // a_ready[p] (k-block pair p) completes once per producing layer 0..8; layer l >= 1 consumes round (l - 1).
+          // Every epilogue thread arrives on pair 0 before pair 1, so pair 1 complete implies pair 0 complete.
           const uint32_t a_par = (a_cnt + (uint32_t)(l - 1)) & 1;
           if (l >= 1) {
-            // N-half 0 overwrites accumulator columns [0,128): both warp groups must have drained them
+            // N-half 0 overwrites accumulator columns [0,128) and needs k-blocks {0,1}: pair 0.  N-half 1 overwrites
+            // [128,256) (drained by the epilogue's second half) and reads all four k-blocks: pair 1.
             const long long w0 = stamp ? clock64() : 0;
-            mbar_wait(&a_ready[0], a_par);
+            mbar_wait(&a_ready[nh], a_par);
             if (stamp) wait_a += clock64() - w0;
           }
-          for (int nh = 0; nh < fwd_nh(l); ++nh) {
-            const uint32_t acc = tmem_base + kTmAcc + (uint32_t)nh * 128u;
-            for (int kb = 0; kb < nk; ++kb) {
-              int ab = -1;             // A k-block in TMEM, or -1 for the shared-memory blocks
-              uint32_t a_smem = 0;
-              int nsteps = 4;
-              if (l == 0 || (l == 5 && kb == 0)) {
-                a_smem = sIn_u;                      // encoded position
-              } else if (l == 9 && kb == 4) {
-                a_smem = sIn_u + kBlockBytes;        // encoded view direction (K = 32)
-                nsteps = 2;
-              } else {
-                ab = (l == 5) ? kb - 1 : kb;
-                if (nh == 0 && ab == 2) {
-                  const long long w0 = stamp ? clock64() : 0;
-                  mbar_wait(&a_ready[1], a_par);
-                  if (stamp) wait_a += clock64() - w0;
-                }
+          for (int kb = 0; kb < nk; ++kb) {
+            int ab = -1;             // A k-block in TMEM, or -1 for the shared-memory blocks
+            uint32_t a_smem = 0;
+            int nsteps = 4;
+            if (l == 0 || (l == 5 && kb == 0)) {
+              a_smem = sIn_u;                      // encoded position
+            } else if (l == 9 && kb == 4) {
+              a_smem = sIn_u + kBlockBytes;        // encoded view direction (K = 32)
+              nsteps = 2;
+            } else {
+              ab = (l == 5) ? kb - 1 : kb;
+              if (nh == 0 && ab == 2) {
+                const long long w0 = stamp ? clock64() : 0;
+                mbar_wait(&a_ready[1], a_par);
+                if (stamp) wait_a += clock64() - w0;
               }
-              const uint32_t s = g % kStages, ph = (g / kStages) & 1;
-              if ((kb & 1) == 0) {  // first chunk of a weight stage
-                const long long w1 = stamp ? clock64() : 0;
-                mbar_wait(&full[s], ph);
-                if (stamp) wait_w += clock64() - w1;
-              }
-              tc_fence_after();
-              const bool stage_done = (kb & 1) || kb == nk - 1;
-              if (leader) {
-                const uint64_t db = desc_kmajor(sW_u + s * kStageBytes + (kb & 1) * kChunkBytes);
-                if (ab >= 0) {
-#pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    umma_bf16_ts(acc, a_tm + (uint32_t)(ab * 32 + k * 8), db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                } else {
-                  const uint64_t da = desc_kmajor(a_smem);
-#pragma unroll 4
-                  for (int k = 0; k < nsteps; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                }
-                if (stage_done) umma_commit(&empty[s]);
-              }
-              __syncwarp();
-              if (stage_done) ++g;
             }
-            if (leader) umma_commit(&acc_full[nh]);
+            const uint32_t s = g % kStages, ph = (g / kStages) & 1;
+            if ((kb & 1) == 0) {  // first chunk of a weight stage
+              const long long w1 = stamp ? clock64() : 0;
+              mbar_wait(&full[s], ph);
+              if (stamp) wait_w += clock64() - w1;
+            }
+            tc_fence_after();
+            const bool stage_done = (kb & 1) || kb == nk - 1;
+            if (leader) {
+              const uint64_t db = desc_kmajor(sW_u + s * kStageBytes + (kb & 1) * kChunkBytes);
+              if (ab >= 0) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16_ts(acc, a_tm + (uint32_t)(ab * 32 + k * 8), db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              } else {
+                const uint64_t da = desc_kmajor(a_smem);
+#pragma unroll 4
+                for (int k = 0; k < nsteps; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              }
+              if (stage_done) umma_commit(&empty[s]);
+            }
             __syncwarp();
+            if (stage_done) ++g;
           }
+          if (leader) umma_commit(&acc_full[nh]);
+          __syncwarp();
           if (stamp && leader) {
             unsigned long long* pr = a.prof + (((int)in_cnt - 1) * kNumFwdLayers + l) * 8;
             pr[1] = clock64();
