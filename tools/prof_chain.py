@@ -58,14 +58,14 @@ for label, cache in (("inference", None), ("training", torch.empty(lib.nerf_mlp_
     p = prof.cpu().view(tiles, 10, 8)
     t0 = int(p[0, 0, 0])
     print(f"--- forward chain timeline ({label}), CTA 0, cycles relative to first layer start")
-    print("tile layer  mma_start  mma_issued  acc_seen  epi_done | mma_span  epi_span  layer_period  wait_act  wait_w")
+    print("tile layer  mma_start  mma_issued  acc_seen  epi_done | mma_span  epi_span  layer_period  wait_act  wait_w  st_wait  st_rest")
     prev = None
     for ti in range(1, tiles):
         for l in range(10):
             a, b, c, d = [int(x) - t0 for x in p[ti, l, :4]]
             period = (a - prev) if prev is not None else 0
             prev = a
-            print(f"{ti:4d} {l:5d} {a:10d} {b:11d} {c:9d} {d:9d} | {b - a:8d} {d - c:9d} {period:9d} {int(p[ti, l, 4]):9d} {int(p[ti, l, 5]):7d}")
+            print(f"{ti:4d} {l:5d} {a:10d} {b:11d} {c:9d} {d:9d} | {b - a:8d} {d - c:9d} {period:9d} {int(p[ti, l, 4]):9d} {int(p[ti, l, 5]):7d} {int(p[ti, l, 6]):8d} {int(p[ti, l, 7]):8d}")
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(5): fwd(cache)

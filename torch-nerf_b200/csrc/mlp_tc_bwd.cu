@@ -27,19 +27,22 @@ using namespace tc;
 // ================================================================================================
 // 1. dgrad chain
 // ================================================================================================
-constexpr int kDgStages = 5;
-constexpr int kDgStageBytes = 2 * kChunkBytes;  // two chunks (128 input features x 64 output features each) per barrier
-constexpr int kDgThreads = 352;  // loader, MMA issuer A, 8 epilogue warps, MMA issuer B
-constexpr int kDgMmaWarpB = 10;
-constexpr int kDgEpiThreads = 256;
-constexpr int kDgSmA = 0;      // 8 warps x 4 KB staging of the bf16 gradient blocks for the bulk stores (the MMA A operand lives in TMEM)
-constexpr int kDgSmW = 32768;
-// tensor memory map (columns): fp32 accumulator [0,256) (two N-halves), A operand buffers [256,384) and [384,512)
-constexpr uint32_t kDgTmA = 256;
-constexpr int kDgSmC = kDgSmW + kDgStages * kDgStageBytes;  // w8row0 (256) | wout (384)
+constexpr int kDgStages = 10;                    // 16 KB weight chunks (128 input features x 64 output features)
+constexpr int kDgEpiWarps = 16;
+constexpr int kDgEpiThreads = kDgEpiWarps * 32;
+constexpr int kDgMmaWarpB = 2 + kDgEpiWarps;
+constexpr int kDgThreads = 32 * (3 + kDgEpiWarps);  // loader, MMA issuer X, 16 epilogue warps, MMA issuer Y
+// shared memory map
+constexpr int kDgSmC = 0;                        // w8row0 (256) | wout (384)
 constexpr int kDgSmBar = kDgSmC + 640 * 4;
-constexpr int kDgSmTotal = kDgSmBar + 256;
+constexpr int kDgSmStage = 4096;                 // 8 warp pairs x 4 KB staging slices for the bulk stores
+constexpr int kDgSmW = kDgSmStage + 32768;       // weight ring
+constexpr int kDgSmTotal = kDgSmW + kDgStages * kChunkBytes;
 constexpr int kDgSmemBytes = kDgSmTotal + 1024;
+static_assert(kDgSmemBytes <= 232448, "shared memory budget");
+// tensor memory map (columns), per slot: fp32 accumulator of one N-half [256 s, +128), A operand (G) [256 s + 128, +128)
+constexpr uint32_t kDgTmSlot = 256;
+constexpr uint32_t kDgTmA = 128;
 
 struct DgradArgs {
   const uint8_t* packed;
@@ -62,46 +65,52 @@ __device__ __forceinline__ void masked_group(const uint32_t (&v)[32], uint32_t n
   }
 }
 
-__device__ __forceinline__ void pack_words(const float (&f)[32], uint32_t* w) {
+__device__ __forceinline__ void pack_words(const float (&f)[32], uint32_t (&w)[16]) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) w[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
 }
 
 // 16 packed words (32 columns) -> four 16-byte chunks of a swizzled tile-image row
-__device__ __forceinline__ void store_words(const uint32_t* w, uint8_t* blk_row, int row, int chunk0) {
+__device__ __forceinline__ void store_words(const uint32_t (&w)[16], uint8_t* blk_row, int row, int chunk0) {
 #pragma unroll
   for (int j = 0; j < 4; ++j)
     *reinterpret_cast<uint4*>(blk_row + (((chunk0 + j) ^ (row & 7)) << 4)) =
         make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
 }
 
+// Same pipeline as mlp_fwd_kernel: two 128-row tiles ("slots") per CTA so that one tile's MMAs run during the other's
+// epilogue, one MMA issuer warp per slot, 16 epilogue warps, weights shared by both slots.
 __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sA = smem + kDgSmA;
+  uint8_t* sStage = smem + kDgSmStage;
   uint8_t* sW = smem + kDgSmW;
   float* sC = reinterpret_cast<float*>(smem + kDgSmC);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDgSmBar);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + kDgStages;
-  uint64_t* a_ready = bars + 2 * kDgStages;  // [4]
-  uint64_t* acc_full = a_ready + 4;          // [2 N-halves of the accumulator]
+  uint64_t* full = bars;                        // [kDgStages]
+  uint64_t* empty = bars + kDgStages;           // [kDgStages] both slots' MMAs on the chunk have completed
+  uint64_t* a_ready = bars + 2 * kDgStages;     // [2] per slot: G operand rewritten in TMEM (input stage + layers 0..7)
+  uint64_t* acc_free = a_ready + 2;             // [2] per slot: N-half 0 pulled out of the accumulator
+  uint64_t* acc_full = acc_free + 2;            // [2] per slot: the MMAs of one N-half have completed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ntiles = num_tiles(a.m);
+  const int64_t npairs = (ntiles + 1) / 2;
   {
-    const float* cg = reinterpret_cast<const float*>(a.packed + kPackedConstOff);
-    for (int i = threadIdx.x; i < 640; i += kDgThreads) sC[i] = __ldg(cg + kCW8Row0 + i);  // w8row0 then wout (contiguous)
+    const float* cgp = reinterpret_cast<const float*>(a.packed + kPackedConstOff);
+    for (int i = threadIdx.x; i < 640; i += kDgThreads) sC[i] = __ldg(cgp + kCW8Row0 + i);  // w8row0 then wout (contiguous)
   }
   if (threadIdx.x == 0) {
     for (int i = 0; i < kDgStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], 2);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], kDgEpiThreads);
-    mbar_init(&acc_full[0], 1);
-    mbar_init(&acc_full[1], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_ready[i], kDgEpiThreads);
+      mbar_init(&acc_free[i], kDgEpiThreads);
+      mbar_init(&acc_full[i], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -113,169 +122,180 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
   const float* sWout = sC + 256;  // fc_out.weight (3,128)
 
   if (warp == 0) {
-    {
-      const bool leader = elect_one();
-      uint32_t g = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint8_t* src = a.packed + kPackedBwdOff;
-        for (int c = 0; c < kBwdChunks / 2; ++c) {  // every (layer, N-half) has an even number of chunks
-          const uint32_t s = g % kDgStages, ph = (g / kDgStages) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
-          if (leader) {
-            mbar_arrive_expect_tx(&full[s], kDgStageBytes);
-            bulk_g2s(sW + s * kDgStageBytes, src, kDgStageBytes, &full[s]);
-          }
-          __syncwarp();
-          src += kDgStageBytes;
-          ++g;
+    const bool leader = elect_one();
+    uint32_t g = 0;
+    for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+      const uint8_t* src = a.packed + kPackedBwdOff;
+      for (int c = 0; c < kBwdChunks; ++c) {
+        const uint32_t s = g % kDgStages, ph = (g / kDgStages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        if (leader) {
+          mbar_arrive_expect_tx(&full[s], kChunkBytes);
+          bulk_g2s(sW + s * kChunkBytes, src, kChunkBytes, &full[s]);
         }
+        __syncwarp();
+        src += kChunkBytes;
+        ++g;
       }
     }
   } else if (warp == 1 || warp == kDgMmaWarpB) {
-    // two MMA issuers (see mlp_tc_fwd.cu): warp 1 issues N-half 0 of every layer, warp kDgMmaWarpB N-half 1, so one
-    // warp's barrier probes overlap the other's MMAs.  Each warp runs in lock step, one elected lane issues.
-    {
-      const int nh = (warp == 1) ? 0 : 1;
-      const bool leader = elect_one();
-      uint32_t g_layer = 0, tile_iter = 0;
-      constexpr uint32_t idesc = make_idesc_bf16(128, false, false);
-      const uint32_t sW_u = smem_u32(sW);
-      const uint32_t acc = tmem_base + (uint32_t)nh * 128u;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_iter) {
-        for (int j = 0; j < kNumBwdLayers; ++j) {
-          const int nk = bwd_nk(j);
-          const uint32_t stages_per_half = (uint32_t)nk / 2;
-          uint32_t g = g_layer + (nh ? stages_per_half : 0u);
-          g_layer += 2 * stages_per_half;
-          const uint32_t a_tm = tmem_base + kDgTmA + (uint32_t)(j & 1) * 128u;  // this layer's A operand (G) in TMEM
-          // a_ready[0] (blocks {0,1}) completes 9 times per tile (input stage + layers 0..7): layer j consumes round j.
-          // a_ready[1] (blocks {2,3}) completes 8 times per tile (layers 0..7): layer j >= 1 consumes round j - 1;
-          // every epilogue thread arrives on pair 0 before pair 1, so pair 1 complete implies pair 0 complete.
-          // N-half 0 overwrites accumulator columns [0,128) (drained before pair 0 is signalled), N-half 1 columns
-          // [128,256) (drained before pair 1 / before the next tile's G9 blocks are signalled).
-          if (nh == 0 || j == 0) mbar_wait(&a_ready[0], (tile_iter + (uint32_t)j) & 1);
-          else mbar_wait(&a_ready[1], (uint32_t)(j - 1) & 1);
+    // one MMA issuer per slot (see mlp_tc_fwd.cu); each warp runs in lock step, one elected lane issues
+    const int slot = (warp == 1) ? 0 : 1;
+    const bool leader = elect_one();
+    uint32_t g = 0, n_a = 0, n_free = 0;
+    constexpr uint32_t idesc = make_idesc_bf16(128, false, false);
+    const uint32_t sW_u = smem_u32(sW);
+    const uint32_t acc = tmem_base + (uint32_t)slot * kDgTmSlot;
+    const uint32_t a_tm = acc + kDgTmA;
+    for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+      for (int j = 0; j < kNumBwdLayers; ++j) {
+        const int nk = bwd_nk(j);
+        for (int h = 0; h < 2; ++h) {
+          if (h == 0) {  // the layer's G operand is in TMEM (and the accumulator has been drained)
+            mbar_wait(&a_ready[slot], n_a & 1);
+            ++n_a;
+          } else {       // N-half 0 is out of the accumulator
+            mbar_wait(&acc_free[slot], n_free & 1);
+            ++n_free;
+          }
 #pragma unroll 1
           for (int kb = 0; kb < nk; ++kb) {
-            if (nh == 0 && kb == 2) mbar_wait(&a_ready[1], (uint32_t)(j - 1) & 1);
             const uint32_t s = g % kDgStages, ph = (g / kDgStages) & 1;
-            if ((kb & 1) == 0) mbar_wait(&full[s], ph);
+            mbar_wait(&full[s], ph);
             tc_fence_after();
             if (leader) {
-              const uint64_t db = desc_kmajor(sW_u + s * kDgStageBytes + (kb & 1) * kChunkBytes);
+              const uint64_t db = desc_kmajor(sW_u + s * kChunkBytes);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_bf16_ts(acc, a_tm + (uint32_t)(kb * 32 + k * 8), db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-              if (kb & 1) umma_commit(&empty[s]);
+              umma_commit(&empty[s]);
             }
             __syncwarp();
-            if (kb & 1) ++g;
+            ++g;
           }
-          if (leader) umma_commit(&acc_full[nh]);
+          if (leader) umma_commit(&acc_full[slot]);
           __syncwarp();
         }
       }
     }
   } else {
+    // 16 epilogue warps = 4 per TMEM lane quarter; per event (slot, N-half h) column group cg owns accumulator
+    // columns [32 cg, +32) = gradient columns [128 h + 32 cg, +32)
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int cg = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t accn[2] = {0, 0};
-    uint8_t* st_slot = sA + (warp - 2) * 4096;  // this warp's 32 rows x 128 B staging slice
-    uint8_t* a_row = st_slot + lane * 128;
+    // warps (cg, cg^1) of one quarter share a 32-row x 128 B staging slice and a named barrier; the slice
+    // leaves through the TMA engine (one 4 KB bulk store), which unlike st.global (32 B/clk/SM through the LSU,
+    // measured) does not hold up the epilogue warps
+    const int pair_id = q * 2 + (cg >> 1);
+    uint8_t* st_slice = sStage + pair_id * 4096;
+    const bool pair_leader = ((cg & 1) == 0) && lane == 0;
+    uint32_t n_full[2] = {0, 0};
     float4* ghead_out = reinterpret_cast<float4*>(a.scratch + scratch_ghead_offset(a.m));
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int64_t grow = tile * kTileM + row;
-      uint8_t* g_tile = a.scratch + (size_t)tile * kGradTileBytes;
-      const uint32_t* mask_tile =
-          reinterpret_cast<const uint32_t*>(a.cache + cache_mask_offset(a.m) + (size_t)tile * kMaskTileBytes);
-      // ---- heads on CUDA cores: gz = g_rgb * rgb (1 - rgb) (sigmoid backward), g_sigma_pre = g_sigma * (sigma_pre > 0)
-      float gz0 = 0.f, gz1 = 0.f, gz2 = 0.f, gsp = 0.f;
-      if (grow < a.m) {
-        const float r0 = __ldg(a.rgb + 3 * grow), r1 = __ldg(a.rgb + 3 * grow + 1), r2 = __ldg(a.rgb + 3 * grow + 2);
-        gz0 = __ldg(a.g_rgb + 3 * grow) * r0 * (1.f - r0);
-        gz1 = __ldg(a.g_rgb + 3 * grow + 1) * r1 * (1.f - r1);
-        gz2 = __ldg(a.g_rgb + 3 * grow + 2) * r2 * (1.f - r2);
-        const uint32_t smask = __ldg(mask_tile + kMaskSigmaWord * kTileM + row);
-        gsp = (smask & 1u) ? __ldg(a.g_sigma + grow) : 0.f;
+
+    // this warp pair's 32 rows of one 64-column block -> HBM; `gdst` = the block's rows [32 q, 32 q + 32)
+    auto stage_store = [&](const uint32_t (&w)[16], uint8_t* gdst) {
+      if (pair_leader) bulk_wait_read<0>();  // the previous store out of the slice has been read
+      __syncwarp();
+      named_bar_sync(2 + pair_id, 64);
+      store_words(w, st_slice + lane * 128, row, 4 * (cg & 1));
+      fence_proxy_async();
+      named_bar_sync(2 + pair_id, 64);
+      if (pair_leader) {
+        bulk_s2g(gdst, st_slice, 4096);
+        bulk_commit();
       }
-      if (half == 0) ghead_out[tile * kTileM + row] = make_float4(gz0, gz1, gz2, gsp);
-      // ---- G9 = (gz . W_out) masked by h9 > 0; this half owns columns [64*half, 64*half + 64) = block `half`
-      {
-        if (lane == 0) bulk_wait_read<0>();  // the previous bulk store out of this warp's staging slice has been read
-        __syncwarp();
-        uint32_t w[32];
+      __syncwarp();
+    };
+
+    for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+      const int64_t tile0 = 2 * pair;
+      float gsp[2];
+      // ---- input stage per slot: heads on CUDA cores, G9 into TMEM
 #pragma unroll
-        for (int gi = 0; gi < 2; ++gi) {
-          const int col0 = half * 64 + gi * 32;
-          const uint32_t mk = __ldg(mask_tile + (64 + 2 * half + gi) * kTileM + row);
-          float f[32];
+      for (int s = 0; s < 2; ++s) {
+        const int64_t tile = tile0 + s;
+        const bool valid = tile < ntiles;
+        const int64_t grow = tile * kTileM + row;
+        const uint32_t* mask_row =
+            reinterpret_cast<const uint32_t*>(a.cache + cache_mask_offset(a.m) + (size_t)tile * kMaskTileBytes) + row;
+        // gz = g_rgb * rgb (1 - rgb) (sigmoid backward), g_sigma_pre = g_sigma * (sigma_pre > 0)
+        float gz0 = 0.f, gz1 = 0.f, gz2 = 0.f;
+        gsp[s] = 0.f;
+        if (grow < a.m) {
+          const float r0 = __ldg(a.rgb + 3 * grow), r1 = __ldg(a.rgb + 3 * grow + 1), r2 = __ldg(a.rgb + 3 * grow + 2);
+          gz0 = __ldg(a.g_rgb + 3 * grow) * r0 * (1.f - r0);
+          gz1 = __ldg(a.g_rgb + 3 * grow + 1) * r1 * (1.f - r1);
+          gz2 = __ldg(a.g_rgb + 3 * grow + 2) * r2 * (1.f - r2);
+          const uint32_t smask = __ldg(mask_row + kMaskSigmaWord * kTileM);
+          gsp[s] = (smask & 1u) ? __ldg(a.g_sigma + grow) : 0.f;
+        }
+        if (cg == 0 && valid) ghead_out[tile * kTileM + row] = make_float4(gz0, gz1, gz2, gsp[s]);
+        // G9 = (gz . W_out) masked by h9 > 0; this thread owns columns [32 cg, 32 cg + 32)
+        const int col0 = 32 * cg;
+        const uint32_t mk = valid ? __ldg(mask_row + (64 + cg) * kTileM) : 0u;
+        float f[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float t = gz0 * sWout[col0 + i];
-            t = fmaf(gz1, sWout[128 + col0 + i], t);
-            t = fmaf(gz2, sWout[256 + col0 + i], t);
-            f[i] = ((mk >> (31 - i)) & 1u) ? 0.f : t;
-          }
-          pack_words(f, w + 16 * gi);
+        for (int i = 0; i < 32; ++i) {
+          float t = gz0 * sWout[col0 + i];
+          t = fmaf(gz1, sWout[128 + col0 + i], t);
+          t = fmaf(gz2, sWout[256 + col0 + i], t);
+          f[i] = ((mk >> (31 - i)) & 1u) ? 0.f : t;
         }
-        tmem_st32(lane_addr + kDgTmA + half * 32, w);  // layer 0 reads A buffer 0
-        store_words(w, a_row, row, 0);
-        store_words(w + 16, a_row, row, 4);
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          bulk_s2g(g_tile + (size_t)(kGradG9 + half) * kBlockBytes + q * 4096, st_slot, 4096);
-          bulk_commit();
-        }
+        uint32_t w[16];
+        pack_words(f, w);
+        tmem_st16(lane_addr + (uint32_t)s * kDgTmSlot + kDgTmA + 16 * cg, w);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&a_ready[0]);  // block pair {0, 1}
+        mbar_arrive(&a_ready[s]);  // also: this thread has drained the slot's previous tile
+        if (valid) stage_store(w, a.scratch + (size_t)tile * kGradTileBytes + (size_t)(kGradG9 + (cg >> 1)) * kBlockBytes + q * 4096);
       }
-      for (int j = 0; j < kNumBwdLayers; ++j) {
-        const uint32_t taddr = lane_addr;
-        const uint32_t a_next = lane_addr + kDgTmA + (uint32_t)((j + 1) & 1) * 128u;
-        const int slot = 8 - j;  // ReLU mask of the layer output this gradient flows into (j >= 1): h7 .. h0
+      uint32_t wh[2][16];  // bf16 pairs of N-half 0, held until half 1's MMAs have stopped reading the G operand
 #pragma unroll 1
-        for (int t = 0; t < 2; ++t) {
-          const int kb = half + 2 * t;  // N-half t, this warp group's 64 columns of it
-          mbar_wait(&acc_full[t], accn[t] & 1);
-          ++accn[t];
-          tc_fence_after();
-          uint32_t v0[32], v1[32];
-          tmem_ld32(taddr + kb * 64, v0);
-          tmem_ld32(taddr + kb * 64 + 32, v1);
-          uint32_t m0 = 0u, m1 = 0u;  // sign-bit masks: 0 = every column passes (layer j = 0 has no ReLU)
-          if (j >= 1) {
-            m0 = __ldg(mask_tile + (slot * 8 + 2 * kb) * kTileM + row);
-            m1 = __ldg(mask_tile + (slot * 8 + 2 * kb + 1) * kTileM + row);
-          }
-          if (lane == 0) bulk_wait_read<0>();
-          __syncwarp();
-          tmem_ld_wait();
-          uint8_t* blk_row = a_row;
-          float f[32];
-          uint32_t w[32];
-          masked_group(v0, m0, gsp, j == 1 ? sW8 + kb * 64 : nullptr, f);
-          pack_words(f, w);
-          masked_group(v1, m1, gsp, j == 1 ? sW8 + kb * 64 + 32 : nullptr, f);
-          pack_words(f, w + 16);
-          if (j < kNumBwdLayers - 1) tmem_st32(a_next + kb * 32, w);
-          store_words(w, blk_row, row, 0);
-          store_words(w + 16, blk_row, row, 4);
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            bulk_s2g(g_tile + (size_t)(2 + 4 * j + kb) * kBlockBytes + q * 4096, st_slot, 4096);
-            bulk_commit();
-          }
-          if (j < kNumBwdLayers - 1) {
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&a_ready[t]);  // block pair {2t, 2t+1}
-          } else {
-            tc_fence_before();
+      for (int j = 0; j < kNumBwdLayers; ++j) {
+        const int slot_m = 8 - j;  // ReLU mask of the layer output this gradient flows into (j >= 1): h7 .. h0
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const int64_t tile = tile0 + s;
+            const bool valid = tile < ntiles;
+            const int col0 = 128 * h + 32 * cg;
+            const uint32_t t_slot = lane_addr + (uint32_t)s * kDgTmSlot;
+            uint32_t mk = 0u;  // sign-bit mask: 0 = every column passes (layer j = 0 has no ReLU)
+            if (j >= 1 && valid)
+              mk = __ldg(reinterpret_cast<const uint32_t*>(a.cache + cache_mask_offset(a.m) + (size_t)tile * kMaskTileBytes) +
+                         row + (slot_m * 8 + 4 * h + cg) * kTileM);
+            mbar_wait(&acc_full[s], n_full[s] & 1);
+            ++n_full[s];
+            tc_fence_after();
+            uint32_t v[32];
+            tmem_ld32(t_slot + 32 * cg, v);
+            tmem_ld_wait();
+            if (h == 0) {
+              tc_fence_before();
+              mbar_arrive(&acc_free[s]);
+            }
+            float f[32];
+            uint32_t w[16];
+            masked_group(v, mk, gsp[s], j == 1 ? sW8 + col0 : nullptr, f);
+            pack_words(f, w);
+            if (h == 0) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) wh[s][i] = w[i];
+            } else if (j < kNumBwdLayers - 1) {
+              tmem_st16(t_slot + kDgTmA + 16 * cg, wh[s]);
+              tmem_st16(t_slot + kDgTmA + 64 + 16 * cg, w);
+              tmem_st_wait();
+              tc_fence_before();
+              mbar_arrive(&a_ready[s]);
+            } else {
+              tc_fence_before();
+            }
+            // gradient block for wgrad
+            if (valid)
+              stage_store(w, a.scratch + (size_t)tile * kGradTileBytes + (size_t)(2 + 4 * j + 2 * h + (cg >> 1)) * kBlockBytes + q * 4096);
           }
         }
       }
@@ -668,7 +688,8 @@ extern "C" int nerf_mlp_bf16_backward(const void* packed_dev, const void* cache_
     a.rgb = rgb_dev, a.g_sigma = g_sigma_dev, a.g_rgb = g_rgb_dev;
     a.scratch = reinterpret_cast<uint8_t*>(scratch_dev);
     a.m = m;
-    const int grid = (int)(ntiles < sms ? ntiles : sms);
+    const int64_t npairs = (ntiles + 1) / 2;  // a CTA works on two tiles at a time
+    const int grid = (int)(npairs < sms ? npairs : sms);
     mlp_dgrad_kernel<<<grid, kDgThreads, kDgSmemBytes, st>>>(a);
     NERF_LAUNCH_CHECK();
   }

@@ -1,27 +1,31 @@
 // K4+K5 on the sm_100a tensor cores: the NeRF MLP forward (network/nerf.py:65-121) as a chain of tcgen05 BF16 MMAs
 // with fp32 accumulation in TMEM; positional encoding (signal_encoder/positional_encoder.py:49-104, as applied by
 // scene/primitives/cube.py:62-69) is computed in-kernel as the first layer's operand; weights are streamed from L2
-// by the TMA engine (cp.async.bulk + mbarrier) through a 4-stage ring of 32 KB stages (two chunks of 128 outputs x 64 inputs).
+// by the TMA engine (cp.async.bulk + mbarrier) through a ring of 16 KB stages (one chunk of 128 outputs x 64 inputs).
 //
-// One CTA per SM, 128 sample rows per tile.  Activations live in TENSOR MEMORY between layers:
+// One CTA per SM works on TWO 128-row tiles at a time ("slots" X and Y).  A layer's output is the next layer's
+// input, so within one tile the tensor pipe has to wait for the epilogue (TMEM -> bias/ReLU -> bf16 -> TMEM) between
+// layers; with two independent tiles the pipe runs tile Y's MMAs while tile X is in its epilogue, and every weight
+// chunk fetched from L2 is used twice.  Activations live in TENSOR MEMORY between layers, per slot s:
 //
-//   TMEM columns [0,256)    fp32 accumulator of the current layer (two N-halves of 128 columns)
-//                [256,384)  A operand buffer 0  (128 rows x 256 bf16 as packed pairs)   \ ping-pong: layer l reads
-//                [384,512)  A operand buffer 1                                          / buffer l&1, writes (l+1)&1
+//   TMEM columns [256 s, +128)        fp32 accumulator of one N-half (128 output columns) of the current layer
+//                [256 s + 128, +128)  A operand: the layer input, 128 rows x 256 bf16 as packed pairs
 //
-//   warp 0      weight loader   1-D bulk copies of pre-swizzled bf16 weight chunks
-//   warps 1,10  MMA issuers     one thread each issues tcgen05.mma (M=128, N=128, K=16) in the TS form: A from TMEM, B from
-//                               shared memory -- this takes the activations off the shared-memory port, which limits
-//                               the SS form to one 128x256x16 MMA per 168 cycles.  A 256-wide layer is two N-halves
-//                               committed separately: while the tensor pipe computes output columns [128,256) the
-//                               epilogue already drains [0,128), and the next layer's first MMAs (which only need the
-//                               k-blocks produced from half 0) start the moment half 1 is issued.
-//   warps 2-9   epilogue        two warps per TMEM lane quarter: tcgen05.ld -> +bias, ReLU -> bf16 pairs -> tcgen05.st
-//                               into the other A buffer, signalled per 64-column k-block; the same warps build the
-//                               encoded inputs of the next tile (those two k-blocks stay in shared memory, SS form)
+//   warp 0      weight loader   1-D bulk copies of pre-swizzled bf16 weight chunks (shared by both slots)
+//   warps 1,18  MMA issuers     one per slot; one elected lane issues tcgen05.mma (M=128, N=128, K=16) in the TS form:
+//                               A from TMEM, B from shared memory -- this takes the activations off the shared-memory
+//                               port, which limits the SS form.  A 256-wide layer is two N-halves through the same
+//                               128 accumulator columns: half 1 starts as soon as the epilogue has pulled half 0 into
+//                               registers (acc_free), and the layer input is overwritten in place once half 1 is done.
+//   warps 2-17  epilogue        four warps per TMEM lane quarter, each thread owns 32 accumulator columns per event
+//                               (slot, N-half): tcgen05.ld -> +bias, ReLU -> bf16 pairs; the half-0 result is held in
+//                               registers and both halves are written with tcgen05.st after half 1 (a_ready).  The
+//                               same warps build the encoded inputs of the next tile pair (those k-blocks stay in
+//                               shared memory, SS form).
 //
-// In training mode the epilogue additionally writes every layer input as a tile image (through a shared-memory staging
-// area and per-warp 4 KB bulk stores) plus ReLU sign-bit masks into the training cache.
+// In training mode the epilogue additionally writes every layer input as a tile image (two warps fill one 32-row x
+// 128 B staging slice, one 4 KB bulk store per slice) plus ReLU sign-bit masks into the training cache -- after the
+// barrier arrives, off the tensor pipe's critical path.
 //
 // Tensor-core layers: fc_in, fc_1..fc_7, fc_8 rows 1..256 (features), fc_9.  The density head (fc_8 row 0,
 // nerf.py:115) and fc_out + sigmoid (nerf.py:119) are fp32 dot products in the epilogues of layers 7 and 9,
@@ -36,24 +40,29 @@
 namespace nerf {
 using namespace tc;
 
-constexpr int kStages = 4;
-constexpr int kStageBytes = 2 * kChunkBytes;  // two chunks (128 output rows x 64 K-columns each) per barrier: every
-                                              // mbarrier probe costs the issuing thread ~125 cycles of dead tensor time
-constexpr int kFwdThreads = 352;   // loader, MMA issuer A, 8 epilogue warps, MMA issuer B
-constexpr int kMmaWarpB = 10;
-constexpr int kEpiThreads = 256;
+constexpr int kMaxStages = 9;
+template <bool kTrain>
+struct FwdCfg {
+  static constexpr int kStages = kTrain ? 7 : 9;  // inference uses the staging area as two more weight stages
+};
+constexpr int kEpiWarps = 16;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kMmaWarpB = 2 + kEpiWarps;
+constexpr int kFwdThreads = 32 * (3 + kEpiWarps);  // loader, MMA issuer X, 16 epilogue warps, MMA issuer Y
 // shared memory map (bytes from the 1024-aligned base)
-constexpr int kSmStage = 0;                     // 8 warps x 4 KB: staging of bf16 activations for the cache (training)
-constexpr int kSmIn = 32768;                    // pe block 16 KB | de block 16 KB (A operands of the SS-form chunks)
-constexpr int kSmW = 65536;                     // weight ring
-constexpr int kSmC = kSmW + kStages * kStageBytes;
-constexpr int kSmX = kSmC + kCFloats * 4;       // 128 x 4 floats: partial sigma / rgb exchange between warp groups
-constexpr int kSmBar = kSmX + 128 * 16;
-constexpr int kSmTotal = kSmBar + 256;
+constexpr int kSmIn = 0;                        // pe block slot X | pe block slot Y | de block (X: chunks 0-3, Y: chunks 4-7)
+constexpr int kSmC = 3 * kBlockBytes;           // fp32 constants
+constexpr int kSmX = kSmC + kCFloats * 4;       // 2 slots x 128 rows x 4 column groups x {rgb0, rgb1, rgb2, sigma} partial sums
+constexpr int kSmBar = kSmX + 2 * 128 * 64;
+constexpr int kSmStage = (kSmBar + 512 + 1023) / 1024 * 1024;  // training: 8 warp pairs x 4 KB staging slices
+constexpr int kSmWTrain = kSmStage + 32768;     // weight ring (training)
+constexpr int kSmWInfer = kSmStage;             // weight ring (inference)
+constexpr int kSmTotal = kSmStage + kMaxStages * kChunkBytes;
 constexpr int kFwdSmemBytes = kSmTotal + 1024;  // + alignment slack
-// tensor memory map (columns)
-constexpr uint32_t kTmAcc = 0;
-constexpr uint32_t kTmA = 256;                  // two A buffers of 128 columns
+static_assert(kFwdSmemBytes <= 232448, "shared memory budget");
+// tensor memory map (columns), per slot
+constexpr uint32_t kTmSlot = 256;
+constexpr uint32_t kTmA = 128;
 
 struct FwdArgs {
   const uint8_t* packed;
@@ -69,13 +78,16 @@ struct FwdArgs {
   uint8_t* cache;       // training cache or null
   unsigned long long* prof;  // optional timeline of CTA 0 (nerf_debug_set_profile_buffer)
   int prof_tiles;
+  int dbg_store;  // debug: 0 normal, 1 skip the training-cache stores, 2 wrap them onto 64 tiles (L2 resident)
 };
 
-// [v | sin(2^l v) | cos(2^l v)]_{l<L} for a 3-vector, written as bf16 into the first NCHUNK 16-byte chunks of a
-// swizzled tile-image row.  Higher octaves come from angle doubling (sin 2a = 2 sin a cos a,
-// cos 2a = (cos a - sin a)(cos a + sin a)); the accumulated error (~2^l ulp) is far below bf16 resolution.
-template <int L, int NCHUNK>
-__device__ __forceinline__ void encode_row(float x, float y, float z, uint8_t* row_ptr, int row) {
+// [v | sin(2^l v) | cos(2^l v)]_{l<L} for a 3-vector, written as bf16 into NCHUNK 16-byte chunks (logical chunks
+// chunk0 .. chunk0 + NCHUNK - 1) of a swizzled tile-image row.  Higher octaves come from angle doubling
+// (sin 2a = 2 sin a cos a, cos 2a = (cos a - sin a)(cos a + sin a)); the accumulated error (~2^l ulp) is far below
+// bf16 resolution.  With kGlobal the same chunks also go to `global_row_ptr` (logical chunks 0 .. NCHUNK - 1).
+template <int L, int NCHUNK, bool kGlobal>
+__device__ __forceinline__ void encode_row(float x, float y, float z, uint8_t* row_ptr, int chunk0,
+                                           uint8_t* global_row_ptr, int row) {
   float v[NCHUNK * 8];
   float sn[3], cs[3];
   v[0] = x, v[1] = y, v[2] = z;
@@ -99,7 +111,8 @@ __device__ __forceinline__ void encode_row(float x, float y, float z, uint8_t* r
   for (int j = 0; j < NCHUNK; ++j) {
     uint4 q = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
                          pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-    *reinterpret_cast<uint4*>(row_ptr + ((j ^ (row & 7)) << 4)) = q;
+    *reinterpret_cast<uint4*>(row_ptr + (((chunk0 + j) ^ (row & 7)) << 4)) = q;
+    if (kGlobal) *reinterpret_cast<uint4*>(global_row_ptr + ((j ^ (row & 7)) << 4)) = q;
   }
 }
 
@@ -127,13 +140,13 @@ __device__ __forceinline__ uint32_t finish_group(const uint32_t (&v)[32], const 
 }
 
 // 32 fp32 values -> 16 packed bf16 pairs
-__device__ __forceinline__ void pack_group(const float (&f)[32], uint32_t* w) {
+__device__ __forceinline__ void pack_group(const float (&f)[32], uint32_t (&w)[16]) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) w[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
 }
 
 // 16 packed words (32 columns) -> four 16-byte chunks of a swizzled tile-image row
-__device__ __forceinline__ void store_words(const uint32_t* w, uint8_t* blk_row, int row, int chunk0) {
+__device__ __forceinline__ void store_words(const uint32_t (&w)[16], uint8_t* blk_row, int row, int chunk0) {
 #pragma unroll
   for (int j = 0; j < 4; ++j)
     *reinterpret_cast<uint4*>(blk_row + (((chunk0 + j) ^ (row & 7)) << 4)) =
@@ -142,37 +155,42 @@ __device__ __forceinline__ void store_words(const uint32_t* w, uint8_t* blk_row,
 
 template <bool kTrain>
 __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
+  constexpr int kStages = FwdCfg<kTrain>::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sStage = smem + kSmStage;
   uint8_t* sIn = smem + kSmIn;
-  uint8_t* sW = smem + kSmW;
+  uint8_t* sStage = smem + kSmStage;
+  uint8_t* sW = smem + (kTrain ? kSmWTrain : kSmWInfer);
   float* sC = reinterpret_cast<float*>(smem + kSmC);
-  float* sX = reinterpret_cast<float*>(smem + kSmX);
+  float4* sX = reinterpret_cast<float4*>(smem + kSmX);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmBar);
-  uint64_t* full = bars;                   // [kStages]
-  uint64_t* empty = bars + kStages;        // [kStages]
-  uint64_t* a_ready = bars + 2 * kStages;  // [2 used] k-block pairs {0,1} and {2,3}: one completion per producing layer
-  uint64_t* in_ready = a_ready + 4;        // [1]   one completion per tile
-  uint64_t* acc_full = in_ready + 1;       // [2 N-halves of the accumulator]
+  uint64_t* full = bars;                      // [kMaxStages] weight chunk landed
+  uint64_t* empty = bars + kMaxStages;        // [kMaxStages] both slots' MMAs on the chunk have completed
+  uint64_t* in_ready = bars + 2 * kMaxStages; // [2] per slot: encoded inputs written, previous tile fully drained
+  uint64_t* a_ready = in_ready + 2;           // [2] per slot: layer input rewritten in TMEM (one completion per layer 0..8)
+  uint64_t* acc_free = a_ready + 2;           // [2] per slot: N-half 0 pulled out of the accumulator
+  uint64_t* acc_full = acc_free + 2;          // [2] per slot: the MMAs of one N-half have completed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ntiles = num_tiles(a.m);
+  const int64_t npairs = (ntiles + 1) / 2;
 
   {
-    const float* cg = reinterpret_cast<const float*>(a.packed + kPackedConstOff);
-    for (int i = threadIdx.x; i < kCFloats; i += kFwdThreads) sC[i] = __ldg(cg + i);
+    const float* cgp = reinterpret_cast<const float*>(a.packed + kPackedConstOff);
+    for (int i = threadIdx.x; i < kCFloats; i += kFwdThreads) sC[i] = __ldg(cgp + i);
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], 2);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], kEpiThreads);
-    mbar_init(in_ready, kEpiThreads);
-    mbar_init(&acc_full[0], 1);
-    mbar_init(&acc_full[1], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&in_ready[i], kEpiThreads);
+      mbar_init(&a_ready[i], kEpiThreads);
+      mbar_init(&acc_free[i], kEpiThreads);
+      mbar_init(&acc_full[i], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -183,64 +201,57 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
 
   if (warp == 0) {
     // ------------------------------------------------------------------ weight loader (warp in lock step, one lane issues)
-    {
-      const bool leader = elect_one();
-      uint32_t g = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint8_t* src = a.packed + kPackedFwdOff;
-        for (int l = 0; l < kNumFwdLayers; ++l) {
-          for (int nh = 0; nh < fwd_nh(l); ++nh) {
-            for (int c0 = 0; c0 < fwd_nk(l); c0 += 2) {
-              const uint32_t bytes = (uint32_t)min(2, fwd_nk(l) - c0) * kChunkBytes;
-              const uint32_t s = g % kStages, ph = (g / kStages) & 1;
-              mbar_wait(&empty[s], ph ^ 1);
-              if (leader) {
-                mbar_arrive_expect_tx(&full[s], bytes);
-                bulk_g2s(sW + s * kStageBytes, src, bytes, &full[s]);
-              }
-              __syncwarp();
-              src += bytes;
-              ++g;
-            }
-          }
+    const bool leader = elect_one();
+    uint32_t g = 0;
+    for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+      const uint8_t* src = a.packed + kPackedFwdOff;
+      for (int c = 0; c < kFwdChunks; ++c) {
+        const uint32_t s = g % kStages, ph = (g / kStages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        if (leader) {
+          mbar_arrive_expect_tx(&full[s], kChunkBytes);
+          bulk_g2s(sW + s * kChunkBytes, src, kChunkBytes, &full[s]);
         }
+        __syncwarp();
+        src += kChunkBytes;
+        ++g;
       }
     }
   } else if (warp == 1 || warp == kMmaWarpB) {
-    // ------------------------------------------------------------------ MMA issuers (two warps)
+    // ------------------------------------------------------------------ MMA issuers (one warp per slot)
     // tcgen05.mma issue is effectively synchronous (the issuing thread is held while its MMA executes) and every
-    // mbarrier probe costs ~125-150 cycles, so a single issuer leaves the tensor pipe idle during each probe.  Warp 1
-    // issues N-half 0 of every layer, warp kMmaWarpB N-half 1: while one polls its barriers the other's MMAs run.
+    // mbarrier probe costs ~125-150 cycles, so each slot has its own issuer: while one polls, the other's MMAs run.
     // Each warp runs its loop in lock step and one elected lane issues.
-    {
-      const int nh = (warp == 1) ? 0 : 1;
-      const bool leader = elect_one();
-      uint32_t g_layer = 0, a_cnt = 0, in_cnt = 0;
-      constexpr uint32_t idesc = make_idesc_bf16(128, false, false);
-      const uint32_t sIn_u = smem_u32(sIn), sW_u = smem_u32(sW);
-      const uint32_t acc = tmem_base + kTmAcc + (uint32_t)nh * 128u;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        // the encoded inputs are ready; all epilogue warps have also left the previous tile (accumulator drained)
-        mbar_wait(in_ready, in_cnt & 1);
-        ++in_cnt;
-        for (int l = 0; l < kNumFwdLayers; ++l) {
-          const int nk = fwd_nk(l);
-          const uint32_t stages_per_half = (uint32_t)(nk + 1) / 2;
-          uint32_t g = g_layer + (nh ? stages_per_half : 0u);  // this warp's first weight stage of the layer
-          g_layer += stages_per_half * (uint32_t)fwd_nh(l);
-          if (nh >= fwd_nh(l)) continue;                      // fc_9 is a single N-half
-          const uint32_t a_tm = tmem_base + kTmA + (uint32_t)(l & 1) * 128u;  // this layer's A operand in TMEM
-          const bool stamp = a.prof != nullptr && blockIdx.x == 0 && (int)in_cnt <= a.prof_tiles && nh == 0;
-          if (stamp && leader) a.prof[(((int)in_cnt - 1) * kNumFwdLayers + l) * 8 + 0] = clock64();
-          long long wait_a = 0, wait_w = 0;
-          // a_ready[p] (k-block pair p) completes once per producing layer 0..8; layer l >= 1 consumes round (l - 1).
-          // Every epilogue thread arrives on pair 0 before pair 1, so pair 1 complete implies pair 0 complete.
-          const uint32_t a_par = (a_cnt + (uint32_t)(l - 1)) & 1;
-          if (l >= 1) {
-            // N-half 0 overwrites accumulator columns [0,128) and needs k-blocks {0,1}: pair 0.  N-half 1 overwrites
-            // [128,256) (drained by the epilogue's second half) and reads all four k-blocks: pair 1.
+    const int slot = (warp == 1) ? 0 : 1;
+    const bool leader = elect_one();
+    uint32_t g = 0, n_in = 0, n_a = 0, n_free = 0;
+    constexpr uint32_t idesc = make_idesc_bf16(128, false, false);
+    const uint32_t sW_u = smem_u32(sW);
+    const uint32_t sPe_u = smem_u32(sIn) + (uint32_t)slot * kBlockBytes;
+    const uint32_t sDe_u = smem_u32(sIn) + 2u * kBlockBytes + (uint32_t)slot * 64u;
+    const uint32_t acc = tmem_base + (uint32_t)slot * kTmSlot;
+    const uint32_t a_tm = acc + kTmA;
+    int iter = 0;
+    for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++iter) {
+      mbar_wait(&in_ready[slot], n_in & 1);
+      ++n_in;
+      for (int l = 0; l < kNumFwdLayers; ++l) {
+        const int nk = fwd_nk(l);
+        const bool stamp = a.prof != nullptr && blockIdx.x == 0 && iter < a.prof_tiles && slot == 0;
+        if (stamp && leader) a.prof[(iter * kNumFwdLayers + l) * 8 + 0] = clock64();
+        long long wait_a = 0, wait_w = 0;
+        for (int h = 0; h < fwd_nh(l); ++h) {
+          {
             const long long w0 = stamp ? clock64() : 0;
-            mbar_wait(&a_ready[nh], a_par);
+            if (h == 0) {
+              if (l >= 1) {  // the epilogue has rewritten this slot's layer input (and drained the accumulator)
+                mbar_wait(&a_ready[slot], n_a & 1);
+                ++n_a;
+              }
+            } else {         // N-half 0 is out of the accumulator
+              mbar_wait(&acc_free[slot], n_free & 1);
+              ++n_free;
+            }
             if (stamp) wait_a += clock64() - w0;
           }
           for (int kb = 0; kb < nk; ++kb) {
@@ -248,28 +259,22 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
             uint32_t a_smem = 0;
             int nsteps = 4;
             if (l == 0 || (l == 5 && kb == 0)) {
-              a_smem = sIn_u;                      // encoded position
+              a_smem = sPe_u;                      // encoded position
             } else if (l == 9 && kb == 4) {
-              a_smem = sIn_u + kBlockBytes;        // encoded view direction (K = 32)
+              a_smem = sDe_u;                      // encoded view direction (K = 32)
               nsteps = 2;
             } else {
               ab = (l == 5) ? kb - 1 : kb;
-              if (nh == 0 && ab == 2) {
-                const long long w0 = stamp ? clock64() : 0;
-                mbar_wait(&a_ready[1], a_par);
-                if (stamp) wait_a += clock64() - w0;
-              }
             }
             const uint32_t s = g % kStages, ph = (g / kStages) & 1;
-            if ((kb & 1) == 0) {  // first chunk of a weight stage
+            {
               const long long w1 = stamp ? clock64() : 0;
               mbar_wait(&full[s], ph);
               if (stamp) wait_w += clock64() - w1;
             }
             tc_fence_after();
-            const bool stage_done = (kb & 1) || kb == nk - 1;
             if (leader) {
-              const uint64_t db = desc_kmajor(sW_u + s * kStageBytes + (kb & 1) * kChunkBytes);
+              const uint64_t db = desc_kmajor(sW_u + s * kChunkBytes);
               if (ab >= 0) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
@@ -279,204 +284,218 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
 #pragma unroll 4
                 for (int k = 0; k < nsteps; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
               }
-              if (stage_done) umma_commit(&empty[s]);
+              umma_commit(&empty[s]);
             }
             __syncwarp();
-            if (stage_done) ++g;
+            ++g;
           }
-          if (leader) umma_commit(&acc_full[nh]);
+          if (leader) umma_commit(&acc_full[slot]);
           __syncwarp();
-          if (stamp && leader) {
-            unsigned long long* pr = a.prof + (((int)in_cnt - 1) * kNumFwdLayers + l) * 8;
-            pr[1] = clock64();
-            pr[4] = (unsigned long long)wait_a;
-            pr[5] = (unsigned long long)wait_w;
-          }
         }
-        a_cnt += 9;
+        if (stamp && leader) {
+          unsigned long long* pr = a.prof + (iter * kNumFwdLayers + l) * 8;
+          pr[1] = clock64();
+          pr[4] = (unsigned long long)wait_a;
+          pr[5] = (unsigned long long)wait_w;
+        }
       }
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
+    // 16 warps = 4 per TMEM lane quarter; per event (slot, N-half h) column group cg owns accumulator columns
+    // [32 cg, +32) = layer output columns [128 h + 32 cg, +32) = half of k-block (2 h + cg/2) of the next layer.
     const int q = warp & 3;             // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;   // warp group: drains k-block `half` of N-half 0 and k-block `2 + half` of N-half 1
+    const int cg = (warp - 2) >> 2;     // column group 0..3
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t accn[2] = {0, 0};  // completions seen per N-half barrier
-    uint8_t* st_slot = sStage + (warp - 2) * 4096;  // this warp's 32 rows x 128 B staging slice
-    uint8_t* st_row = st_slot + lane * 128;
-    int tile_iter = 0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_iter) {
-      const int64_t grow = tile * kTileM + row;
-      const bool stamp = a.prof != nullptr && blockIdx.x == 0 && tile_iter < a.prof_tiles && warp == 2 && lane == 0;
-      uint8_t* cache_tile = kTrain ? a.cache + (size_t)tile * kCacheTileBytes : nullptr;
-      uint32_t* mask_tile =
-          kTrain ? reinterpret_cast<uint32_t*>(a.cache + cache_mask_offset(a.m) + (size_t)tile * kMaskTileBytes) : nullptr;
-      // ---- encoded inputs (cube.py:62-69): half 0 encodes the point, half 1 the view direction
+    // training: warps (cg, cg^1) of one quarter share a 32-row x 128 B staging slice and a named barrier; the slice
+    // leaves through the TMA engine (one 4 KB bulk store), which unlike st.global (32 B/clk/SM through the LSU,
+    // measured) does not hold up the epilogue warps
+    const int pair_id = q * 2 + (cg >> 1);
+    uint8_t* st_slice = sStage + pair_id * 4096;
+    const bool pair_leader = ((cg & 1) == 0) && lane == 0;
+    uint32_t n_full[2] = {0, 0};
+    int iter = 0;
+
+    // this warp pair's 32 rows of one 64-column block -> HBM; `gdst` = the block's rows [32 q, 32 q + 32)
+    auto stage_store = [&](const uint32_t (&w)[16], uint8_t* gdst) {
+      if (pair_leader) bulk_wait_read<0>();  // the previous store out of the slice has been read
+      __syncwarp();
+      named_bar_sync(2 + pair_id, 64);
+      store_words(w, st_slice + lane * 128, row, 4 * (cg & 1));
+      fence_proxy_async();
+      named_bar_sync(2 + pair_id, 64);
+      if (pair_leader) {
+        bulk_s2g(gdst, st_slice, 4096);
+        bulk_commit();
+      }
+      __syncwarp();
+    };
+
+    for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++iter) {
+      const bool stamp = a.prof != nullptr && blockIdx.x == 0 && iter < a.prof_tiles && warp == 2 && lane == 0;
+      const int64_t tile0 = 2 * pair;
+      // ---- encoded inputs (cube.py:62-69): groups 0/1 encode the points of slots X/Y, groups 2/3 the view directions
       {
-        float x = 0.f, y = 0.f, z = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
+        const int s_in = cg & 1;
+        const bool is_pe = cg < 2;
+        const int64_t tile = tile0 + s_in;
+        const int64_t grow = tile * kTileM + row;
+        float x = 0.f, y = 0.f, z = 0.f;
         if (grow < a.m) {
           if (a.pts != nullptr) {
-            if (half == 0) {
-              x = __ldg(a.pts + 3 * grow), y = __ldg(a.pts + 3 * grow + 1), z = __ldg(a.pts + 3 * grow + 2);
-            } else {
-              dx = __ldg(a.dirs + 3 * grow), dy = __ldg(a.dirs + 3 * grow + 1), dz = __ldg(a.dirs + 3 * grow + 2);
-            }
+            const float* src = is_pe ? a.pts : a.dirs;
+            x = __ldg(src + 3 * grow), y = __ldg(src + 3 * grow + 1), z = __ldg(src + 3 * grow + 2);
           } else {
             const int64_t ray = grow / a.s;
-            dx = __ldg(a.ray_d + 3 * ray), dy = __ldg(a.ray_d + 3 * ray + 1), dz = __ldg(a.ray_d + 3 * ray + 2);
-            if (half == 0) {
+            x = __ldg(a.ray_d + 3 * ray), y = __ldg(a.ray_d + 3 * ray + 1), z = __ldg(a.ray_d + 3 * ray + 2);
+            if (is_pe) {
               const float tt = __ldg(a.t + grow);
               // stratified_sampler.py:126: o + t*d, product and sum rounded separately
-              x = __fadd_rn(__ldg(a.ray_o + 3 * ray), __fmul_rn(tt, dx));
-              y = __fadd_rn(__ldg(a.ray_o + 3 * ray + 1), __fmul_rn(tt, dy));
-              z = __fadd_rn(__ldg(a.ray_o + 3 * ray + 2), __fmul_rn(tt, dz));
+              x = __fadd_rn(__ldg(a.ray_o + 3 * ray), __fmul_rn(tt, x));
+              y = __fadd_rn(__ldg(a.ray_o + 3 * ray + 1), __fmul_rn(tt, y));
+              z = __fadd_rn(__ldg(a.ray_o + 3 * ray + 2), __fmul_rn(tt, z));
             }
           }
         }
-        if (kTrain) {
-          if (lane == 0) bulk_wait_read<0>();  // the previous tile's stores (incl. the one out of the input block) are read
-          __syncwarp();
-        }
-        if (half == 0) encode_row<10, 8>(x, y, z, sIn + row * 128, row);
-        else encode_row<4, 4>(dx, dy, dz, sIn + kBlockBytes + row * 128, row);
-        fence_proxy_async();
-        if (kTrain) {
-          __syncwarp();
-          if (lane == 0) {
-            const int blk = half == 0 ? kCachePe : kCacheDe;
-            bulk_s2g(cache_tile + (size_t)blk * kBlockBytes + q * 4096, sIn + half * kBlockBytes + q * 4096, 4096);
-            bulk_commit();
-          }
-        }
-        mbar_arrive(in_ready);
-      }
-      float sigma_part = 0.f;
-      float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
-      for (int l = 0; l < kNumFwdLayers; ++l) {
-        const uint32_t taddr = lane_addr + kTmAcc;
-        const uint32_t a_next = lane_addr + kTmA + (uint32_t)((l + 1) & 1) * 128u;  // next layer's A operand
-        const float* bias = sC + ((l < 8) ? kCBias + 256 * l : (l == 8 ? kCBias8 : kCBias9));
-        if (l < 9) {
-#pragma unroll 1
-          for (int t = 0; t < 2; ++t) {
-            // N-half t of the layer is complete: this warp drains its 64 columns of it = k-block kb of the next layer
-            const int kb = half + 2 * t;
-            mbar_wait(&acc_full[t], accn[t] & 1);
-            ++accn[t];
-            tc_fence_after();
-            if (stamp && t == 0) a.prof[((tile_iter * kNumFwdLayers + l) * 8) + 2] = clock64();
-            uint32_t v0[32], v1[32];
-            tmem_ld32(taddr + kb * 64, v0);
-            tmem_ld32(taddr + kb * 64 + 32, v1);
-            if (kTrain) {
-              if (lane == 0) bulk_wait_read<0>();  // this warp's previous bulk store out of its staging slice has been read
-              __syncwarp();
-            }
-            tmem_ld_wait();
-            float f[32];
-            uint32_t w[32];
-            uint32_t neg;
-            if (l == 8) neg = finish_group<false>(v0, bias + kb * 64, f);
-            else neg = finish_group<true>(v0, bias + kb * 64, f);
-            if (l == 7) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) sigma_part = fmaf(f[i], sC[kCW8Row0 + kb * 64 + i], sigma_part);
-            }
-            if (kTrain && l < 8) mask_tile[(l * 8 + 2 * kb) * kTileM + row] = neg;
-            pack_group(f, w);
-            if (l == 8) neg = finish_group<false>(v1, bias + kb * 64 + 32, f);
-            else neg = finish_group<true>(v1, bias + kb * 64 + 32, f);
-            if (l == 7) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) sigma_part = fmaf(f[i], sC[kCW8Row0 + kb * 64 + 32 + i], sigma_part);
-            }
-            if (kTrain && l < 8) mask_tile[(l * 8 + 2 * kb + 1) * kTileM + row] = neg;
-            pack_group(f, w + 16);
-            tmem_st32(a_next + kb * 32, w);  // 64 bf16 = 32 packed columns of this row
-            if (kTrain) {
-              store_words(w, st_row, row, 0);
-              store_words(w + 16, st_row, row, 4);
-              fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) {
-                const int blk = (l < 8 ? cache_h(l) : kCacheFeat) + kb;
-                bulk_s2g(cache_tile + (size_t)blk * kBlockBytes + q * 4096, st_slot, 4096);
-                bulk_commit();
-              }
-            }
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&a_ready[t]);  // k-block pair t = {2t, 2t+1}
-          }
-          if (l == 7 && half == 1) sX[row * 4 + 3] = sigma_part;
-          if (stamp) a.prof[((tile_iter * kNumFwdLayers + l) * 8) + 3] = clock64();
-        } else {
-          // fc_9 output (128 columns = one N-half): this warp group owns columns [64*half, 64*half + 64)
-          mbar_wait(&acc_full[0], accn[0] & 1);
-          ++accn[0];
-          tc_fence_after();
-          if (stamp) a.prof[((tile_iter * kNumFwdLayers + l) * 8) + 2] = clock64();
-          uint32_t v0[32], v1[32];
-          tmem_ld32(taddr + half * 64, v0);
-          tmem_ld32(taddr + half * 64 + 32, v1);
+        const bool to_cache = kTrain && tile < ntiles;
+        uint8_t* cache_row = kTrain ? a.cache + (size_t)tile * kCacheTileBytes + row * 128 : nullptr;
+        if (is_pe) {
           if (kTrain) {
-            if (lane == 0) bulk_wait_read<0>();
+            if (lane == 0) bulk_wait_read<0>();  // the previous pair's store out of this pe block has been read
             __syncwarp();
           }
-          tmem_ld_wait();
-          float f[32];
-          uint32_t w[32];
-          uint32_t neg = finish_group<true>(v0, bias + half * 64, f);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            rgb0 = fmaf(f[i], sC[kCWout + half * 64 + i], rgb0);
-            rgb1 = fmaf(f[i], sC[kCWout + 128 + half * 64 + i], rgb1);
-            rgb2 = fmaf(f[i], sC[kCWout + 256 + half * 64 + i], rgb2);
-          }
+          encode_row<10, 8, false>(x, y, z, sIn + s_in * kBlockBytes + row * 128, 0, nullptr, row);
+          fence_proxy_async();
           if (kTrain) {
-            mask_tile[(64 + 2 * half) * kTileM + row] = neg;
-            pack_group(f, w);
-          }
-          neg = finish_group<true>(v1, bias + half * 64 + 32, f);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            rgb0 = fmaf(f[i], sC[kCWout + half * 64 + 32 + i], rgb0);
-            rgb1 = fmaf(f[i], sC[kCWout + 128 + half * 64 + 32 + i], rgb1);
-            rgb2 = fmaf(f[i], sC[kCWout + 256 + half * 64 + 32 + i], rgb2);
-          }
-          if (kTrain) {
-            mask_tile[(64 + 2 * half + 1) * kTileM + row] = neg;
-            pack_group(f, w + 16);
-            store_words(w, st_row, row, 0);
-            store_words(w + 16, st_row, row, 4);
-            fence_proxy_async();
             __syncwarp();
-            if (lane == 0) {
-              bulk_s2g(cache_tile + (size_t)(kCacheH9 + half) * kBlockBytes + q * 4096, st_slot, 4096);
+            if (lane == 0 && to_cache) {
+              bulk_s2g(a.cache + (size_t)tile * kCacheTileBytes + (size_t)kCachePe * kBlockBytes + q * 4096,
+                       sIn + s_in * kBlockBytes + q * 4096, 4096);
               bulk_commit();
             }
           }
-          tc_fence_before();
-          if (half == 1) {
-            sX[row * 4 + 0] = rgb0;
-            sX[row * 4 + 1] = rgb1;
-            sX[row * 4 + 2] = rgb2;
-          }
-          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-          if (half == 0) {
-            const float4 o = *reinterpret_cast<const float4*>(sX + row * 4);
-            const float sp = sigma_part + o.w + sC[kCB8_0];
-            if (grow < a.m) {
-              a.sigma[grow] = fmaxf(sp, 0.f);                                  // nerf.py:115
-              a.rgb[3 * grow] = 1.f / (1.f + __expf(-(rgb0 + o.x + sC[kCBout])));    // nerf.py:119
-              a.rgb[3 * grow + 1] = 1.f / (1.f + __expf(-(rgb1 + o.y + sC[kCBout + 1])));
-              a.rgb[3 * grow + 2] = 1.f / (1.f + __expf(-(rgb2 + o.z + sC[kCBout + 2])));
-            }
-            if (kTrain) mask_tile[kMaskSigmaWord * kTileM + row] = (grow < a.m && sp > 0.f) ? 1u : 0u;
-          }
-          if (stamp) a.prof[((tile_iter * kNumFwdLayers + l) * 8) + 3] = clock64();
+        } else {
+          if (to_cache)
+            encode_row<4, 4, true>(x, y, z, sIn + 2 * kBlockBytes + row * 128, 4 * s_in,
+                                   cache_row + (size_t)kCacheDe * kBlockBytes, row);
+          else
+            encode_row<4, 4, false>(x, y, z, sIn + 2 * kBlockBytes + row * 128, 4 * s_in, nullptr, row);
+          fence_proxy_async();
         }
+        mbar_arrive(&in_ready[0]);  // all 512 threads on both: inputs written AND this thread has left the previous pair
+        mbar_arrive(&in_ready[1]);
+      }
+      float sigma_part[2] = {0.f, 0.f};
+      uint32_t wh[2][16];  // bf16 pairs of N-half 0, held until half 1's MMAs have stopped reading the layer input
+#pragma unroll 1
+      for (int l = 0; l < kNumFwdLayers - 1; ++l) {
+        const float* bias = sC + ((l < 8) ? kCBias + 256 * l : kCBias8);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const int col0 = 128 * h + 32 * cg;
+            const uint32_t t_slot = lane_addr + (uint32_t)s * kTmSlot;
+            mbar_wait(&acc_full[s], n_full[s] & 1);
+            ++n_full[s];
+            tc_fence_after();
+            if (stamp && s == 0 && h == 0) a.prof[((iter * kNumFwdLayers + l) * 8) + 2] = clock64();
+            uint32_t v[32];
+            tmem_ld32(t_slot + 32 * cg, v);
+            tmem_ld_wait();
+            if (h == 0) {
+              tc_fence_before();
+              mbar_arrive(&acc_free[s]);
+            }
+            float f[32];
+            uint32_t w[16];
+            uint32_t neg;
+            if (l == 8) neg = finish_group<false>(v, bias + col0, f);
+            else neg = finish_group<true>(v, bias + col0, f);
+            pack_group(f, w);
+            if (h == 0) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) wh[s][j] = w[j];
+            } else {
+              tmem_st16(t_slot + kTmA + 16 * cg, wh[s]);       // output columns [32 cg, +32)
+              tmem_st16(t_slot + kTmA + 64 + 16 * cg, w);      // output columns [128 + 32 cg, +32)
+              tmem_st_wait();
+              tc_fence_before();
+              mbar_arrive(&a_ready[s]);
+            }
+            if (l == 7) {
+              float acc_s = sigma_part[s];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) acc_s = fmaf(f[i], sC[kCW8Row0 + col0 + i], acc_s);
+              sigma_part[s] = acc_s;
+            }
+            if (kTrain && tile0 + s < ntiles) {
+              // layer input of the backward pass as a tile image + the ReLU sign bits
+              uint8_t* cache_tile = a.cache + (size_t)(a.dbg_store == 2 ? (int64_t)(2 * blockIdx.x + s) : (tile0 + s)) * kCacheTileBytes;
+              if (l < 8) {
+                uint32_t* mask_row = reinterpret_cast<uint32_t*>(a.cache + cache_mask_offset(a.m) +
+                                                                 (size_t)(tile0 + s) * kMaskTileBytes) + row;
+                mask_row[(l * 8 + 4 * h + cg) * kTileM] = neg;
+              }
+              int blk = (l < 8 ? cache_h(l) : kCacheFeat) + 2 * h + (cg >> 1);
+              if (a.dbg_store == 2) blk &= 3;  // debug: every CTA rewrites its own 128 KB window (L2 resident)
+              if (a.dbg_store != 1) stage_store(w, cache_tile + (size_t)blk * kBlockBytes + q * 4096);
+            }
+            if (stamp && s == 0 && h == 1) a.prof[((iter * kNumFwdLayers + l) * 8) + 3] = clock64();
+          }
+        }
+      }
+      // ---- fc_9 output (128 columns = one N-half): this thread owns columns [32 cg, 32 cg + 32)
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int l = kNumFwdLayers - 1;
+        const int col0 = 32 * cg;
+        const int64_t tile = tile0 + s;
+        const int64_t grow = tile * kTileM + row;
+        mbar_wait(&acc_full[s], n_full[s] & 1);
+        ++n_full[s];
+        tc_fence_after();
+        if (stamp && s == 0) a.prof[((iter * kNumFwdLayers + l) * 8) + 2] = clock64();
+        uint32_t v[32];
+        tmem_ld32(lane_addr + (uint32_t)s * kTmSlot + col0, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        float f[32];
+        const uint32_t neg = finish_group<true>(v, sC + kCBias9 + col0, f);
+        float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          rgb0 = fmaf(f[i], sC[kCWout + col0 + i], rgb0);
+          rgb1 = fmaf(f[i], sC[kCWout + 128 + col0 + i], rgb1);
+          rgb2 = fmaf(f[i], sC[kCWout + 256 + col0 + i], rgb2);
+        }
+        if (cg != 0) sX[(s * 128 + row) * 4 + cg] = make_float4(rgb0, rgb1, rgb2, sigma_part[s]);
+        uint32_t* mask_row = nullptr;
+        if (kTrain && tile < ntiles) {
+          mask_row = reinterpret_cast<uint32_t*>(a.cache + cache_mask_offset(a.m) + (size_t)tile * kMaskTileBytes) + row;
+          uint32_t w[16];
+          mask_row[(64 + cg) * kTileM] = neg;
+          pack_group(f, w);
+          stage_store(w, a.cache + (size_t)tile * kCacheTileBytes + (size_t)(kCacheH9 + (cg >> 1)) * kBlockBytes + q * 4096);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        if (cg == 0) {
+          float sp = sigma_part[s] + sC[kCB8_0];
+#pragma unroll
+          for (int g = 1; g < 4; ++g) {
+            const float4 o = sX[(s * 128 + row) * 4 + g];
+            rgb0 += o.x, rgb1 += o.y, rgb2 += o.z, sp += o.w;
+          }
+          if (grow < a.m) {
+            a.sigma[grow] = fmaxf(sp, 0.f);                                  // nerf.py:115
+            a.rgb[3 * grow] = 1.f / (1.f + __expf(-(rgb0 + sC[kCBout])));    // nerf.py:119
+            a.rgb[3 * grow + 1] = 1.f / (1.f + __expf(-(rgb1 + sC[kCBout + 1])));
+            a.rgb[3 * grow + 2] = 1.f / (1.f + __expf(-(rgb2 + sC[kCBout + 2])));
+          }
+          if (kTrain && tile < ntiles) mask_row[kMaskSigmaWord * kTileM] = (grow < a.m && sp > 0.f) ? 1u : 0u;
+        }
+        if (stamp && s == 0) a.prof[((iter * kNumFwdLayers + l) * 8) + 3] = clock64();
       }
     }
     if (kTrain) {
@@ -494,6 +513,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
 
 static unsigned long long* g_prof_buf = nullptr;
 static int g_prof_tiles = 0;
+static int g_dbg_store = 0;
 
 }  // namespace nerf
 
@@ -501,7 +521,8 @@ using namespace nerf;
 
 extern "C" int nerf_debug_set_profile_buffer(unsigned long long* buf_dev, int tiles) {
   g_prof_buf = buf_dev;
-  g_prof_tiles = tiles;
+  g_prof_tiles = tiles & 0xffff;
+  g_dbg_store = tiles >> 16;  // debug only: store mode in the high bits
   return NERF_OK;
 }
 
@@ -527,8 +548,9 @@ extern "C" int nerf_mlp_bf16_forward(const void* packed_dev, const float* pts_de
   a.cache = reinterpret_cast<uint8_t*>(cache_dev);
   a.prof = g_prof_buf;
   a.prof_tiles = g_prof_tiles;
-  const int64_t ntiles = num_tiles(m);
-  const int grid = (int)((ntiles < sm_count()) ? ntiles : sm_count());
+  a.dbg_store = g_dbg_store;
+  const int64_t npairs = (num_tiles(m) + 1) / 2;  // a CTA works on two tiles at a time
+  const int grid = (int)((npairs < sm_count()) ? npairs : sm_count());
   if (cache_dev)
     mlp_fwd_kernel<true><<<grid, kFwdThreads, kFwdSmemBytes, as_stream(stream)>>>(a);
   else
