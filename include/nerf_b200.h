@@ -194,6 +194,11 @@ int nerf_debug_set_profile_buffer(unsigned long long* buf_dev, int tiles);
  * default 7).  Lets bench.py time the HBM-bound wgrad kernel alone on a scratch buffer a full backward has filled. */
 int nerf_debug_set_bwd_phases(int mask);
 
+/* debugging aid: when buf_dev != NULL every CTA of the next wgrad launches records 8 values into
+ * buf_dev[cta*16 + k]: globaltimer ns k=0 start, 1 last accumulator complete, 2 end; k=3 first unit, 4 segment count,
+ * 5/6 tiles of the first / second segment.  Pass NULL to switch it off. */
+int nerf_debug_set_wgrad_profile(unsigned long long* buf_dev);
+
 /* micro-benchmark: `blocks` CTAs each issue `iters` x 4 tcgen05.mma (M=128, N=n, K=16) -- mode bit 0: A operand from TMEM instead of
  * shared memory; bit 1: tcgen05.commit after every group of 4; bit 2: probe a completed mbarrier before every group -- while `bg_warps` extra warps each perform `bg_iters` tcgen05.ld
  * (bg_store = 0) or tcgen05.st (1) of 32 lanes x 32 columns.  cycles_dev[block] = SM cycles of the MMA thread,

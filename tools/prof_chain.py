@@ -49,12 +49,16 @@ prof = torch.zeros(tiles * 10 * 8, dtype=torch.int64, device="cuda")
 def fwd(cache=None):
     tn._lib.check(lib.nerf_mlp_bf16_forward(P(packed, torch.uint8), None, None, P(ray_o), P(ray_d), P(t), s, m, P(sig), P(rgb),
                                             P(cache, torch.uint8) if cache is not None else None, tn._lib.stream()), "fwd")
-for label, cache in (("inference", None), ("training", torch.empty(lib.nerf_mlp_bf16_cache_bytes(m), dtype=torch.uint8, device="cuda"))):
+train_cache = torch.empty(lib.nerf_mlp_bf16_cache_bytes(m), dtype=torch.uint8, device="cuda")
+cases = [("inference", None, 0), ("training", train_cache, 0)]
+if "--nostore" in sys.argv:
+    cases.append(("training, block stores skipped (debug)", train_cache, 1))
+for label, cache, mode in cases:
     fwd(cache); torch.cuda.synchronize()
-    lib.nerf_debug_set_profile_buffer(VP(prof.data_ptr()), tiles)
+    lib.nerf_debug_set_profile_buffer(VP(prof.data_ptr()), tiles | (mode << 16))
     prof.zero_()
     fwd(cache); torch.cuda.synchronize()
-    lib.nerf_debug_set_profile_buffer(None, 0)
+    lib.nerf_debug_set_profile_buffer(None, mode << 16)
     p = prof.cpu().view(tiles, 10, 8)
     t0 = int(p[0, 0, 0])
     print(f"--- forward chain timeline ({label}), CTA 0, cycles relative to first layer start")
@@ -71,3 +75,4 @@ for label, cache in (("inference", None), ("training", torch.empty(lib.nerf_mlp_
     for _ in range(5): fwd(cache)
     ev1.record(); torch.cuda.synchronize()
     print(f"{label}: {ev0.elapsed_time(ev1)/5*1e3:.0f} us per launch of {m} rows")
+    lib.nerf_debug_set_profile_buffer(None, 0)

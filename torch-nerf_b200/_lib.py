@@ -65,6 +65,7 @@ _PROTOTYPES = {
     "nerf_selftest_umma": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
     "nerf_debug_set_profile_buffer": (c_int, [_P, c_int]),
     "nerf_debug_set_bwd_phases": (c_int, [c_int]),
+    "nerf_debug_set_wgrad_profile": (c_int, [_P]),
     "nerf_selftest_mma_rate": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
 }
 

@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&a_ready[s]);  // also: this thread has drained the slot's previous tile
-        if (valid) stage_store(w, a.scratch + (size_t)tile * kGradTileBytes + (size_t)(kGradG9 + (cg >> 1)) * kBlockBytes + q * 4096);
+        if (valid) stage_store(w, a.scratch + (size_t)tile * kGradTileBytes + grad_slice_off(kGradG9 + (cg >> 1), q));
       }
       uint32_t wh[2][16];  // bf16 pairs of N-half 0, held until half 1's MMAs have stopped reading the G operand
 #pragma unroll 1
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
             }
             // gradient block for wgrad
             if (valid)
-              stage_store(w, a.scratch + (size_t)tile * kGradTileBytes + (size_t)(2 + 4 * j + 2 * h + (cg >> 1)) * kBlockBytes + q * 4096);
+              stage_store(w, a.scratch + (size_t)tile * kGradTileBytes + grad_slice_off(2 + 4 * j + 2 * h + (cg >> 1), q));
           }
         }
       }
@@ -319,7 +319,9 @@ struct WUnit {
   int n_gblk;      // 0 (head-only unit), 2 or 4 (64 output features each)
   int x_blk0;      // first X block in the cache tile image (contiguous blocks)
   int n_xblk;      // full 64-column X blocks
-  int x_extra;     // extra narrow block (view-direction encoding, 32 columns) or -1
+  int x_extra;     // extra narrow block (view-direction encoding, 32 columns) right after the full blocks, or -1
+  int n_xload;     // X-side blocks fetched per slice, contiguous from x_blk0 (MMA blocks, then blocks only the head reads)
+  int head_xblk;   // first X-side block (relative to x_blk0) the head sums read
   int param_w;     // weight gradient slot
   int w_row0;      // first output row in the weight tensor
   int w_col0;      // first input column
@@ -328,26 +330,36 @@ struct WUnit {
   int param_b;     // bias slot or -1
   int b_off;
   int cost;        // relative time per tile for the work partition (blocks streamed; more for CUDA-core-only units)
-  int head;        // 0: none; 1: density head (d fc_8.weight[0,:], d fc_8.bias[0]) from g_sigma_pre and the X slices
-                   // 2: fc_out (d fc_out.weight, d fc_out.bias) from gz and the X slices (X = h9, no MMA)
+  int head;        // 0: none; 1: density head (d fc_8.weight[0,:], d fc_8.bias[0]) from g_sigma_pre and the unit's X blocks
+                   // 2: fc_out (d fc_out.weight, d fc_out.bias) from gz and the two h9 blocks fetched after the MMA blocks
 };
-constexpr int kNumWUnits = 12;
+constexpr int kNumWUnits = 11;
 __constant__ WUnit c_wunits[kNumWUnits];
 
-constexpr int kWgStages = 5;
-constexpr int kWgSlice = 4096;            // 32 rows of one block
-constexpr int kWgHeadOff = 9 * kWgSlice;  // 32 x float4 head gradients
-constexpr int kWgStageBytes = kWgHeadOff + 1024;
-constexpr int kWgThreads = 192;
-constexpr int kWgSmBar = kWgStages * kWgStageBytes;
-constexpr int kWgSmemBytes = kWgSmBar + 256 + 1024;
+// The ring holds as many stages as fit: one stage = the 32-row slices of every block a unit streams (+ 512 B of head
+// gradients), so units that stream few bytes per slice get a deeper ring and keep the same number of bytes in flight.
+constexpr int kWgSlice = 4096;             // 32 rows of one block
+constexpr int kWgRingBytes = 188 * 1024;
+constexpr int kWgMaxStages = 16;
+constexpr int kWgCudaWarps = 8;            // bias / head sums and the accumulator flush
+constexpr int kWgThreads = 32 * (2 + kWgCudaWarps);
+constexpr int kWgSmBar = kWgRingBytes;
+constexpr int kWgSmemBytes = kWgSmBar + 512 + 1024;
+static_assert(kWgSmemBytes <= 232448, "shared memory budget");
 
 struct WgradArgs {
   const uint8_t* cache;
   const uint8_t* scratch;
   ParamPtrs grads;
   int64_t m;
+  unsigned long long* prof;  // optional per-CTA timeline (nerf_debug_set_wgrad_profile): 8 values per CTA
 };
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 
 struct Segment {
   int unit;
@@ -386,27 +398,82 @@ __device__ inline int build_segments(int64_t ntiles, Segment* seg) {
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
+// 8 consecutive bf16 columns (one 16-byte chunk of a tile-image row)
+__device__ __forceinline__ void unpack8(const uint4& c, float (&x)[8]) {
+  x[0] = bf16_lo(c.x), x[1] = bf16_hi(c.x), x[2] = bf16_lo(c.y), x[3] = bf16_hi(c.y);
+  x[4] = bf16_lo(c.z), x[5] = bf16_hi(c.z), x[6] = bf16_lo(c.w), x[7] = bf16_hi(c.w);
+}
+
+// column sums of ROWS rows (r0 ..) of the 16-byte column group `cg` of a staged operand (blocks kWgSlice apart)
+template <int ROWS>
+__device__ __forceinline__ void col_sums(const uint8_t* blocks, int cg, int r0, float (&acc)[8]) {
+  uint4 c[ROWS];
+#pragma unroll
+  for (int rr = 0; rr < ROWS; ++rr) {
+    const int r = r0 + rr;
+    c[rr] = *reinterpret_cast<const uint4*>(blocks + (cg >> 3) * 4096 + r * 128 + (((cg ^ r) & 7) << 4));
+  }
+#pragma unroll
+  for (int rr = 0; rr < ROWS; ++rr) {
+    float x[8];
+    unpack8(c[rr], x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += x[i];
+  }
+}
+
+// head weight gradients: acc[j][i] += g_j[row] * x[row][8 cg + i]; NH = 1 takes g = gh[row].w (density head),
+// NH = 3 takes {x, y, z} (fc_out)
+template <int ROWS, int NH>
+__device__ __forceinline__ void head_sums(const uint8_t* blocks, const float4* gh, int cg, int r0, float (&acc)[3][8]) {
+  uint4 c[ROWS];
+  float4 gv[ROWS];
+#pragma unroll
+  for (int rr = 0; rr < ROWS; ++rr) {
+    const int r = r0 + rr;
+    c[rr] = *reinterpret_cast<const uint4*>(blocks + (cg >> 3) * 4096 + r * 128 + (((cg ^ r) & 7) << 4));
+    gv[rr] = gh[r];
+  }
+#pragma unroll
+  for (int rr = 0; rr < ROWS; ++rr) {
+    float x[8];
+    unpack8(c[rr], x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (NH == 1) {
+        acc[0][i] = fmaf(gv[rr].w, x[i], acc[0][i]);
+      } else {
+        acc[0][i] = fmaf(gv[rr].x, x[i], acc[0][i]);
+        acc[1][i] = fmaf(gv[rr].y, x[i], acc[1][i]);
+        acc[2][i] = fmaf(gv[rr].z, x[i], acc[2][i]);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgSmBar);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + kWgStages;
-  uint64_t* acc_done = bars + 2 * kWgStages;
-  uint64_t* acc_free = acc_done + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 1);
+  uint64_t* full = bars;                      // [kWgMaxStages]
+  uint64_t* empty = bars + kWgMaxStages;      // [kWgMaxStages]
+  uint64_t* acc_done = bars + 2 * kWgMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
   __shared__ Segment segs[kNumWUnits];
   __shared__ int nseg_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ntiles = num_tiles(a.m);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kWgStages; ++i) {
+    for (int i = 0; i < kWgMaxStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1 + 4);  // MMA commit + the four CUDA-core warps
+      mbar_init(&empty[i], 1 + kWgCudaWarps);  // MMA commit + the CUDA-core warps
     }
     mbar_init(acc_done, 1);
-    mbar_init(acc_free, 128);
     fence_barrier_init();
     nseg_s = build_segments(ntiles, segs);
   }
@@ -416,195 +483,217 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int nseg = nseg_s;
+  if (a.prof != nullptr && threadIdx.x == 64) {
+    unsigned long long* pr = a.prof + blockIdx.x * 16;
+    pr[0] = global_ns();
+    pr[3] = (unsigned long long)segs[0].unit;
+    pr[4] = (unsigned long long)nseg;
+    pr[5] = (unsigned long long)(segs[0].tile1 - segs[0].tile0);
+    pr[6] = nseg > 1 ? (unsigned long long)(segs[1].tile1 - segs[1].tile0) : 0ull;
+  }
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ loader: 32-row slices of every block
-    {
+  for (int si = 0; si < nseg; ++si) {
+    const WUnit u = c_wunits[segs[si].unit];
+    const int64_t tile0 = segs[si].tile0, tile1 = segs[si].tile1;
+    const int nxb = u.n_xload;
+    const uint32_t head_off = (uint32_t)(u.n_gblk + nxb) * kWgSlice;
+    const uint32_t bytes = head_off + (u.head ? 512u : 0u);
+    const uint32_t stage_bytes = (bytes + 1023u) & ~1023u;
+    const uint32_t nst = min((uint32_t)kWgMaxStages, (uint32_t)kWgRingBytes / stage_bytes);
+
+    if (warp == 0) {
+      // ---------------------------------------------------------------- loader: 32-row slices of every block
       const bool leader = elect_one();
       uint32_t g = 0;
+      long long ld_wait = 0;
+      const long long ld_t0 = a.prof ? clock64() : 0;
       const uint8_t* ghead = a.scratch + scratch_ghead_offset(a.m);
-      for (int si = 0; si < nseg; ++si) {
-        const WUnit u = c_wunits[segs[si].unit];
-        const int nxb = u.n_xblk + (u.x_extra >= 0 ? 1 : 0);
-        const uint32_t bytes = (uint32_t)(u.n_gblk + nxb) * kWgSlice + (u.head ? 512u : 0u);
-        for (int64_t tile = segs[si].tile0; tile < segs[si].tile1; ++tile) {
-          const uint8_t* gsrc = a.scratch + (size_t)tile * kGradTileBytes + (size_t)u.g_blk0 * kBlockBytes;
-          const uint8_t* xsrc = a.cache + (size_t)tile * kCacheTileBytes;
-          for (int sl = 0; sl < 4; ++sl) {
-            const uint32_t s = g % kWgStages, ph = (g / kWgStages) & 1;
-            mbar_wait(&empty[s], ph ^ 1);
-            if (leader) {
-              mbar_arrive_expect_tx(&full[s], bytes);
-              uint8_t* dst = smem + s * kWgStageBytes;
-              for (int b = 0; b < u.n_gblk; ++b)
-                bulk_g2s(dst + b * kWgSlice, gsrc + (size_t)b * kBlockBytes + sl * kWgSlice, kWgSlice, &full[s]);
-              uint8_t* xdst = dst + u.n_gblk * kWgSlice;
-              for (int b = 0; b < u.n_xblk; ++b)
-                bulk_g2s(xdst + b * kWgSlice, xsrc + (size_t)(u.x_blk0 + b) * kBlockBytes + sl * kWgSlice, kWgSlice, &full[s]);
-              if (u.x_extra >= 0)
-                bulk_g2s(xdst + u.n_xblk * kWgSlice, xsrc + (size_t)u.x_extra * kBlockBytes + sl * kWgSlice, kWgSlice, &full[s]);
-              if (u.head) bulk_g2s(dst + kWgHeadOff, ghead + ((size_t)tile * kTileM + sl * 32) * 16, 512, &full[s]);
-            }
-            __syncwarp();
-            ++g;
+      for (int64_t tile = tile0; tile < tile1; ++tile) {
+        const uint8_t* gtile = a.scratch + (size_t)tile * kGradTileBytes;
+        const uint8_t* xtile = a.cache + (size_t)tile * kCacheTileBytes;
+        for (int sl = 0; sl < 4; ++sl) {
+          const uint32_t s = g % nst, ph = (g / nst) & 1;
+          const long long w0 = a.prof ? clock64() : 0;
+          mbar_wait(&empty[s], ph ^ 1);
+          if (a.prof) ld_wait += clock64() - w0;
+          if (leader) {
+            // slice-major tiles: the pieces of consecutive blocks of one slice are contiguous -> one copy per operand
+            mbar_arrive_expect_tx(&full[s], bytes);
+            uint8_t* dst = smem + s * stage_bytes;
+            if (u.n_gblk) bulk_g2s(dst, gtile + grad_slice_off(u.g_blk0, sl), (uint32_t)u.n_gblk * kWgSlice, &full[s]);
+            uint8_t* xdst = dst + u.n_gblk * kWgSlice;
+            bulk_g2s(xdst, xtile + cache_slice_off(u.x_blk0, sl), (uint32_t)u.n_xload * kWgSlice, &full[s]);
+            if (u.head) bulk_g2s(dst + head_off, ghead + ((size_t)tile * kTileM + sl * 32) * 16, 512, &full[s]);
           }
+          __syncwarp();
+          ++g;
         }
       }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (MN-major operands)
-    {
+      if (a.prof && leader && si == 0) {
+        a.prof[blockIdx.x * 16 + 8] = (unsigned long long)ld_wait;
+        a.prof[blockIdx.x * 16 + 9] = (unsigned long long)(clock64() - ld_t0);
+      }
+    } else if (warp == 1) {
+      // ---------------------------------------------------------------- MMA issuer (MN-major operands)
       const bool leader = elect_one();
       uint32_t g = 0;
       const uint32_t sm_u = smem_u32(smem);
-      for (int si = 0; si < nseg; ++si) {
-        const WUnit u = c_wunits[segs[si].unit];
-        const int nhalf = u.n_gblk / 2;
-        const uint32_t n_main = (uint32_t)u.n_xblk * 64u;
-        const uint32_t idesc_main = make_idesc_bf16(n_main, true, true);
-        const uint32_t idesc_extra = make_idesc_bf16(32, true, true);
-        if (si > 0) mbar_wait(acc_free, (uint32_t)(si - 1) & 1);
-        tc_fence_after();
-        bool first = true;
-        for (int64_t tile = segs[si].tile0; tile < segs[si].tile1; ++tile) {
-          for (int sl = 0; sl < 4; ++sl) {
-            const uint32_t s = g % kWgStages, ph = (g / kWgStages) & 1;
-            mbar_wait(&full[s], ph);
-            tc_fence_after();
-            const uint32_t st = sm_u + s * kWgStageBytes;
-            const uint32_t xb = st + u.n_gblk * kWgSlice;
-            if (leader) {
-#pragma unroll
-              for (int k = 0; k < 2; ++k) {
-                for (int h = 0; h < nhalf; ++h) {
-                  const uint64_t da = desc_mnmajor(st + (2 * h) * kWgSlice + k * 2048, kWgSlice);
-                  const uint64_t db = desc_mnmajor(xb + k * 2048, kWgSlice);
-                  umma_bf16(tmem_base + h * 256, da, db, idesc_main, (first && k == 0) ? 0u : 1u);
-                  if (u.x_extra >= 0) {
-                    const uint64_t de = desc_mnmajor(xb + u.n_xblk * kWgSlice + k * 2048, kWgSlice);
-                    umma_bf16(tmem_base + h * 256 + n_main, da, de, idesc_extra, (first && k == 0) ? 0u : 1u);
-                  }
-                }
-              }
-              umma_commit(&empty[s]);
-            }
-            first = false;
-            __syncwarp();
-            ++g;
-          }
-        }
-        if (leader) umma_commit(acc_done);
-        __syncwarp();
-      }
-    }
-  } else {
-    // ------------------------------------------------------------------ bias / head sums on CUDA cores + accumulator flush
-    const int q = warp & 3;
-    const int tid = (warp - 2) * 32 + lane;  // 0..127
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t g = 0;
-    for (int si = 0; si < nseg; ++si) {
-      const WUnit u = c_wunits[segs[si].unit];
-      const bool do_bias = u.param_b >= 0 && tid < u.n_gblk * 32;  // (units with a bias have hsplit == 1)
-      // heads: 2 columns per thread; with fewer than 128 column pairs (fc_out: 64) the rows are split instead
-      const int head_pairs = u.n_xblk * 32;
-      const bool do_head = u.head != 0;
-      const int hsplit = (u.head != 0 && head_pairs < 128) ? 128 / head_pairs : 1;  // 1 or 2
-      const int hrows = 32 / hsplit;
-      const int hrow0 = (tid / (128 / hsplit)) * hrows;
-      const int col = 2 * (tid % (128 / hsplit));  // this thread's column pair, in G (bias) and in X (heads)
-      const uint32_t coff = (uint32_t)(col >> 6) * kWgSlice + ((col & 63) & 7) * 2;
-      const uint32_t chunk = (uint32_t)((col & 63) >> 3);
-      float b0 = 0.f, b1 = 0.f;                                                 // bias column sums
-      float h00 = 0.f, h01 = 0.f, h10 = 0.f, h11 = 0.f, h20 = 0.f, h21 = 0.f;  // head sums [j][column of the pair]
-      float hb = 0.f;                                                           // head bias sums (threads 0..3)
-      for (int64_t tile = segs[si].tile0; tile < segs[si].tile1; ++tile) {
+      const int nhalf = u.n_gblk / 2;
+      const uint32_t n_main = (uint32_t)u.n_xblk * 64u;
+      const uint32_t idesc_main = make_idesc_bf16(n_main, true, true);
+      const uint32_t idesc_extra = make_idesc_bf16(32, true, true);
+      bool first = true;
+      long long mma_wait = 0;
+      const long long mma_t0 = a.prof ? clock64() : 0;
+      for (int64_t tile = tile0; tile < tile1; ++tile) {
         for (int sl = 0; sl < 4; ++sl) {
-          const uint32_t s = g % kWgStages, ph = (g / kWgStages) & 1;
+          const uint32_t s = g % nst, ph = (g / nst) & 1;
+          const long long w0 = a.prof ? clock64() : 0;
           mbar_wait(&full[s], ph);
-          const uint8_t* st = smem + s * kWgStageBytes;
-          if (do_bias) {
-            const uint8_t* gs = st + coff;
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r) {
-              const uint32_t w = *reinterpret_cast<const uint32_t*>(gs + r * 128 + (((chunk ^ (uint32_t)(r & 7)) & 7u) << 4));
-              b0 += bf16_lo(w);
-              b1 += bf16_hi(w);
-            }
-          }
-          if (u.head) {
-            const float4* gh = reinterpret_cast<const float4*>(st + kWgHeadOff);
-            if (do_head) {
-              const uint8_t* xs = st + u.n_gblk * kWgSlice + coff;
-#pragma unroll 8
-              for (int rr = 0; rr < hrows; ++rr) {
-                const int r = hrow0 + rr;
-                const uint32_t w = *reinterpret_cast<const uint32_t*>(xs + r * 128 + (((chunk ^ (uint32_t)(r & 7)) & 7u) << 4));
-                const float x0 = bf16_lo(w), x1 = bf16_hi(w);
-                const float4 gv = gh[r];
-                if (u.head == 1) {
-                  h00 = fmaf(gv.w, x0, h00);
-                  h01 = fmaf(gv.w, x1, h01);
-                } else {
-                  h00 = fmaf(gv.x, x0, h00), h01 = fmaf(gv.x, x1, h01);
-                  h10 = fmaf(gv.y, x0, h10), h11 = fmaf(gv.y, x1, h11);
-                  h20 = fmaf(gv.z, x0, h20), h21 = fmaf(gv.z, x1, h21);
+          if (a.prof) mma_wait += clock64() - w0;
+          tc_fence_after();
+          const uint32_t st = sm_u + s * stage_bytes;
+          const uint32_t xb = st + u.n_gblk * kWgSlice;
+          if (leader) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              for (int h = 0; h < nhalf; ++h) {
+                const uint64_t da = desc_mnmajor(st + (2 * h) * kWgSlice + k * 2048, kWgSlice);
+                const uint64_t db = desc_mnmajor(xb + k * 2048, kWgSlice);
+                umma_bf16(tmem_base + h * 256, da, db, idesc_main, (first && k == 0) ? 0u : 1u);
+                if (u.x_extra >= 0) {
+                  const uint64_t de = desc_mnmajor(xb + u.n_xblk * kWgSlice + k * 2048, kWgSlice);
+                  umma_bf16(tmem_base + h * 256 + n_main, da, de, idesc_extra, (first && k == 0) ? 0u : 1u);
                 }
               }
             }
-            if (tid < 4) {
-              const float* ghf = reinterpret_cast<const float*>(gh);
-#pragma unroll 8
-              for (int r = 0; r < 32; ++r) hb += ghf[4 * r + tid];
-            }
+            umma_commit(&empty[s]);
+          }
+          first = false;
+          __syncwarp();
+          ++g;
+        }
+      }
+      if (leader) umma_commit(acc_done);
+      __syncwarp();
+      if (a.prof && leader && si == 0) {
+        a.prof[blockIdx.x * 16 + 10] = (unsigned long long)mma_wait;
+        a.prof[blockIdx.x * 16 + 11] = (unsigned long long)(clock64() - mma_t0);
+      }
+    } else {
+      // ---------------------------------------------------------------- bias / head sums on CUDA cores + accumulator flush
+      // 256 threads; thread t owns one 16-byte column group (8 bf16 columns) and a share of the slice's 32 rows
+      const int t = threadIdx.x - 64;
+      const int b_ncg = u.param_b >= 0 ? u.n_gblk * 8 : 0;  // column groups of the bias sums over G: 32, 16 or none
+      const int h_ncg = u.head == 1 ? 32 : (u.head == 2 ? 16 : 0);  // column groups of the head sums: density over 4 X blocks, fc_out over h9
+      float bacc[8], hacc[3][8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) bacc[i] = hacc[0][i] = hacc[1][i] = hacc[2][i] = 0.f;
+      float hb = 0.f;  // head bias sums (threads 0..127: one row and component each)
+      const int b_cg = b_ncg ? t % b_ncg : 0, b_rows = b_ncg / 8, b_r0 = b_ncg ? (t / b_ncg) * b_rows : 0;
+      const int h_cg = h_ncg ? t % h_ncg : 0, h_rows = h_ncg / 8, h_r0 = h_ncg ? (t / h_ncg) * h_rows : 0;
+      uint32_t g = 0;
+      long long cc_wait = 0;
+      const long long cc_t0 = a.prof ? clock64() : 0;
+      for (int64_t tile = tile0; tile < tile1; ++tile) {
+        for (int sl = 0; sl < 4; ++sl) {
+          const uint32_t s = g % nst, ph = (g / nst) & 1;
+          const long long w0 = a.prof ? clock64() : 0;
+          mbar_wait(&full[s], ph);
+          if (a.prof) cc_wait += clock64() - w0;
+          const uint8_t* st = smem + s * stage_bytes;
+          if (b_ncg == 32) col_sums<4>(st, b_cg, b_r0, bacc);
+          else if (b_ncg == 16) col_sums<2>(st, b_cg, b_r0, bacc);
+          if (u.head) {
+            const float4* gh = reinterpret_cast<const float4*>(st + head_off);
+            const uint8_t* xs = st + (u.n_gblk + u.head_xblk) * kWgSlice;
+            if (u.head == 1) head_sums<4, 1>(xs, gh, h_cg, h_r0, hacc);  // 4 X blocks
+            else head_sums<2, 3>(xs, gh, h_cg, h_r0, hacc);              // 2 X blocks
+            if (t < 128) hb += reinterpret_cast<const float*>(gh)[t];  // row t/4, component t%4 of {gz0, gz1, gz2, g_sigma_pre}
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&empty[s]);
           ++g;
         }
       }
-      if (do_bias) {
-        float* db = a.grads.p[u.param_b] + u.b_off;
-        atomicAdd(db + col, b0);
-        atomicAdd(db + col + 1, b1);
+      if (a.prof && threadIdx.x == 64 && si == 0) {
+        a.prof[blockIdx.x * 16 + 12] = (unsigned long long)cc_wait;
+        a.prof[blockIdx.x * 16 + 13] = (unsigned long long)(clock64() - cc_t0);
+        a.prof[blockIdx.x * 16 + 14] = (unsigned long long)g;
+      }
+      if (b_ncg) {
+        float* db = a.grads.p[u.param_b] + u.b_off + 8 * b_cg;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(db + i, bacc[i]);
+      }
+      if (u.head) {  // lanes with equal (lane & 3) hold the same head-gradient component
+        hb += __shfl_xor_sync(0xffffffffu, hb, 4);
+        hb += __shfl_xor_sync(0xffffffffu, hb, 8);
+        hb += __shfl_xor_sync(0xffffffffu, hb, 16);
       }
       if (u.head == 1) {
-        if (do_head) {
-          atomicAdd(a.grads.p[W_8] + col, h00);  // d fc_8.weight[0, col]
-          atomicAdd(a.grads.p[W_8] + col + 1, h01);
-        }
-        if (tid == 3) atomicAdd(a.grads.p[B_8], hb);  // d fc_8.bias[0] = sum g_sigma_pre
+        float* dw = a.grads.p[W_8] + 8 * h_cg;  // d fc_8.weight[0, :]
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(dw + i, hacc[0][i]);
+        if (t < 128 && lane == 3) atomicAdd(a.grads.p[B_8], hb);  // d fc_8.bias[0] = sum g_sigma_pre
       } else if (u.head == 2) {
-        if (do_head) {
-          float* dw = a.grads.p[W_OUT];
-          atomicAdd(dw + col, h00), atomicAdd(dw + col + 1, h01);
-          atomicAdd(dw + kH + col, h10), atomicAdd(dw + kH + col + 1, h11);
-          atomicAdd(dw + 2 * kH + col, h20), atomicAdd(dw + 2 * kH + col + 1, h21);
-        }
-        if (tid < 3) atomicAdd(a.grads.p[B_OUT] + tid, hb);
+        float* dw = a.grads.p[W_OUT] + 8 * h_cg;
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) atomicAdd(dw + j * kH + i, hacc[j][i]);
+        if (t < 128 && lane < 3) atomicAdd(a.grads.p[B_OUT] + lane, hb);
       }
-      // flush the accumulator of this segment
+      // flush the accumulator of this segment: two warps per TMEM lane quarter alternate over the 32-column chunks
       mbar_wait(acc_done, (uint32_t)si & 1);
       tc_fence_after();
+      if (a.prof != nullptr && threadIdx.x == 64 && si == nseg - 1) a.prof[blockIdx.x * 16 + 1] = global_ns();
+      const int q = warp & 3, wsel = (warp - 2) >> 2;
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
       const int nhalf = u.n_gblk / 2;
       const int ncols = u.n_xblk * 64 + (u.x_extra >= 0 ? 32 : 0);
+      const bool vec = ((u.w_ld & 3) == 0) && ((u.w_col0 & 3) == 0);
       float* dw = a.grads.p[u.param_w];
+      int item = 0;
       for (int h = 0; h < nhalf; ++h) {
         const int out_row = u.w_row0 + h * 128 + q * 32 + lane;
         float* dst = dw + (size_t)out_row * u.w_ld + u.w_col0;
-        for (int c0 = 0; c0 < ncols; c0 += 32) {
+        for (int c0 = 0; c0 < ncols; c0 += 32, ++item) {
+          if ((item & 1) != wsel) continue;
           uint32_t v[32];
           tmem_ld32(lane_addr + h * 256 + c0, v);
           tmem_ld_wait();
+          if (vec && c0 + 32 <= u.valid_cols) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c0 + i < u.valid_cols) atomicAdd(dst + c0 + i, __uint_as_float(v[i]));
+            for (int i = 0; i < 32; i += 4)
+              red_add_v4(dst + c0 + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                         __uint_as_float(v[i + 3]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c0 + i < u.valid_cols) atomicAdd(dst + c0 + i, __uint_as_float(v[i]));
+          }
         }
       }
       tc_fence_before();
-      mbar_arrive(acc_free);
+    }
+    // ---- segment boundary: the next unit uses another ring geometry, so the ring is drained and its barriers start over
+    __syncthreads();
+    if (si + 1 < nseg) {
+      if (threadIdx.x == 0) {
+        for (int i = 0; i < kWgMaxStages; ++i) {
+          mbar_inval(&full[i]);
+          mbar_inval(&empty[i]);
+          mbar_init(&full[i], 1);
+          mbar_init(&empty[i], 1 + kWgCudaWarps);
+        }
+        fence_barrier_init();
+      }
+      __syncthreads();
+      tc_fence_after();
     }
   }
+  if (a.prof != nullptr && threadIdx.x == 64) a.prof[blockIdx.x * 16 + 2] = global_ns();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -615,20 +704,22 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
 
 static void build_wunits(WUnit* u) {
   int n = 0;
-  auto add = [&](int g0, int ng, int x0, int nx, int xe, int pw, int row0, int col0, int ld, int valid, int pb, int boff,
-                 int head) {
-    const int cost = ng > 0 ? ng + nx + (xe >= 0 ? 1 : 0) : 5;  // fc_out streams 2 blocks but is CUDA-core bound
-    u[n++] = WUnit{g0, ng, x0, nx, xe, pw, row0, col0, ld, valid, pb, boff, cost, head};
+  // cost = relative time per tile for the work partition: blocks streamed per slice, corrected by measurement
+  // (tools/prof_wgrad.py) for the units whose slices are short or that carry CUDA-core head sums
+  auto add = [&](int g0, int ng, int x0, int nx, int xe, int nload, int pw, int row0, int col0, int ld, int valid, int pb,
+                 int boff, int head, int head_xblk, int cost) {
+    u[n++] = WUnit{g0, ng, x0, nx, xe, nload, head_xblk, pw, row0, col0, ld, valid, pb, boff, cost, head};
   };
-  add(grad_g(0), 4, kCachePe, 1, -1, W_IN, 0, 0, kP, kP, B_IN, 0, 0);                      // fc_in : G0 x pe
-  for (int l = 1; l <= 4; ++l) add(grad_g(l), 4, cache_h(l - 1), 4, -1, 2 * l, 0, 0, kF, kF, 2 * l + 1, 0, 0);  // fc_1..4
-  add(grad_g(5), 4, kCachePe, 1, -1, W_5, 0, 0, kP + kF, kP, B_5, 0, 0);                   // fc_5, position columns
-  add(grad_g(5), 4, cache_h(4), 4, -1, W_5, 0, kP, kP + kF, kF, -1, 0, 0);                 // fc_5, h4 columns
-  add(grad_g(6), 4, cache_h(5), 4, -1, W_6, 0, 0, kF, kF, B_6, 0, 0);
-  add(grad_g(7), 4, cache_h(6), 4, -1, W_7, 0, 0, kF, kF, B_7, 0, 0);
-  add(kGradG8, 4, cache_h(7), 4, -1, W_8, 1, 0, kF, kF, B_8, 1, 1);                        // fc_8 rows 1..256 + density row
-  add(kGradG9, 2, kCacheFeat, 4, kCacheDe, W_9, 0, 0, kF + kV, kF + kV, B_9, 0, 0);        // fc_9 : G9 x [feat | de]
-  add(0, 0, kCacheH9, 2, -1, W_OUT, 0, 0, kH, 0, -1, 0, 2);                                // fc_out (CUDA cores only)
+  add(grad_g(0), 4, kCachePe, 1, -1, 1, W_IN, 0, 0, kP, kP, B_IN, 0, 0, 0, 64);                      // fc_in : G0 x pe
+  for (int l = 1; l <= 4; ++l) add(grad_g(l), 4, cache_h(l - 1), 4, -1, 4, 2 * l, 0, 0, kF, kF, 2 * l + 1, 0, 0, 0, 80);  // fc_1..4
+  add(grad_g(5), 4, kCachePe, 1, -1, 1, W_5, 0, 0, kP + kF, kP, B_5, 0, 0, 0, 64);                   // fc_5, position columns
+  add(grad_g(5), 4, cache_h(4), 4, -1, 4, W_5, 0, kP, kP + kF, kF, -1, 0, 0, 0, 80);                 // fc_5, h4 columns
+  add(grad_g(6), 4, cache_h(5), 4, -1, 4, W_6, 0, 0, kF, kF, B_6, 0, 0, 0, 80);
+  add(grad_g(7), 4, cache_h(6), 4, -1, 4, W_7, 0, 0, kF, kF, B_7, 0, 0, 0, 80);
+  add(kGradG8, 4, cache_h(7), 4, -1, 4, W_8, 1, 0, kF, kF, B_8, 1, 1, 0, 88);                        // fc_8 rows 1..256 + density row
+  // fc_9 : G9 x [feat | de], and fc_out from gz x h9 on the CUDA cores (feat, de, h9 are consecutive cache blocks)
+  static_assert(kCacheDe == kCacheFeat + 4 && kCacheH9 == kCacheDe + 1, "fc_9 unit fetches feat, de, h9 with one copy");
+  add(kGradG9, 2, kCacheFeat, 4, kCacheDe, 7, W_9, 0, 0, kF + kV, kF + kV, B_9, 0, 2, 5, 84);
 }
 
 __global__ void zero_grads_kernel(ParamPtrs g) {
@@ -640,11 +731,17 @@ __global__ void zero_grads_kernel(ParamPtrs g) {
 }
 
 static bool g_wunits_ready = false;
+static unsigned long long* g_wgrad_prof = nullptr;
 static int g_bwd_phase_mask = 7;  // bit 0: zero the gradients, bit 1: dgrad chain, bit 2: wgrad (profiling aid)
 
 }  // namespace nerf
 
 using namespace nerf;
+
+extern "C" int nerf_debug_set_wgrad_profile(unsigned long long* buf_dev) {
+  g_wgrad_prof = buf_dev;
+  return NERF_OK;
+}
 
 extern "C" int nerf_debug_set_bwd_phases(int mask) {
   g_bwd_phase_mask = mask;
@@ -699,6 +796,7 @@ extern "C" int nerf_mlp_bf16_backward(const void* packed_dev, const void* cache_
     a.scratch = reinterpret_cast<const uint8_t*>(scratch_dev);
     a.grads = gp;
     a.m = m;
+    a.prof = g_wgrad_prof;
     mlp_wgrad_kernel<<<sms, kWgThreads, kWgSmemBytes, st>>>(a);
     NERF_LAUNCH_CHECK();
   }

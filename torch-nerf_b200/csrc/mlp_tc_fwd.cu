@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
           }
         }
         const bool to_cache = kTrain && tile < ntiles;
-        uint8_t* cache_row = kTrain ? a.cache + (size_t)tile * kCacheTileBytes + row * 128 : nullptr;
+        uint8_t* cache_tile_in = kTrain ? a.cache + (size_t)tile * kCacheTileBytes : nullptr;
         if (is_pe) {
           if (kTrain) {
             if (lane == 0) bulk_wait_read<0>();  // the previous pair's store out of this pe block has been read
@@ -370,15 +370,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
           if (kTrain) {
             __syncwarp();
             if (lane == 0 && to_cache) {
-              bulk_s2g(a.cache + (size_t)tile * kCacheTileBytes + (size_t)kCachePe * kBlockBytes + q * 4096,
-                       sIn + s_in * kBlockBytes + q * 4096, 4096);
+              bulk_s2g(cache_tile_in + cache_slice_off(kCachePe, q), sIn + s_in * kBlockBytes + q * 4096, 4096);
               bulk_commit();
             }
           }
         } else {
           if (to_cache)
             encode_row<4, 4, true>(x, y, z, sIn + 2 * kBlockBytes + row * 128, 4 * s_in,
-                                   cache_row + (size_t)kCacheDe * kBlockBytes, row);
+                                   cache_tile_in + cache_slice_off(kCacheDe, q) + lane * 128, row);
           else
             encode_row<4, 4, false>(x, y, z, sIn + 2 * kBlockBytes + row * 128, 4 * s_in, nullptr, row);
           fence_proxy_async();
@@ -440,7 +439,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
               }
               int blk = (l < 8 ? cache_h(l) : kCacheFeat) + 2 * h + (cg >> 1);
               if (a.dbg_store == 2) blk &= 3;  // debug: every CTA rewrites its own 128 KB window (L2 resident)
-              if (a.dbg_store != 1) stage_store(w, cache_tile + (size_t)blk * kBlockBytes + q * 4096);
+              if (a.dbg_store != 1) stage_store(w, cache_tile + cache_slice_off(blk, q));
             }
             if (stamp && s == 0 && h == 1) a.prof[((iter * kNumFwdLayers + l) * 8) + 3] = clock64();
           }
@@ -477,7 +476,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
           uint32_t w[16];
           mask_row[(64 + cg) * kTileM] = neg;
           pack_group(f, w);
-          stage_store(w, a.cache + (size_t)tile * kCacheTileBytes + (size_t)(kCacheH9 + (cg >> 1)) * kBlockBytes + q * 4096);
+          stage_store(w, a.cache + (size_t)tile * kCacheTileBytes + cache_slice_off(kCacheH9 + (cg >> 1), q));
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         if (cg == 0) {

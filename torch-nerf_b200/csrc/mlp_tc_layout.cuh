@@ -1,12 +1,16 @@
 // Fixed geometry and memory layouts of the bf16 tensor-core MLP path (NeRF(63, 27, 256), network/nerf.py:49-59).
 //
 // HBM layouts ("tile images", see tc_common.cuh): everything the training step stages in HBM is stored as
-// 128-row x 64-column bf16 blocks (16 KB, 128B-swizzled) so that 1-D bulk copies (TMA engine) move them and the
+// 128-row x 64-column bf16 blocks (128B-swizzled rows) so that 1-D bulk copies (TMA engine) move them and the
 // very same bytes serve as K-major operands (forward / dgrad chains) and MN-major operands (wgrad).
 //
-//   packed weights : [forward chunks][dgrad (transposed) chunks][fp32 constants]
+//   packed weights : [forward chunks][dgrad (transposed) chunks][fp32 constants]; a chunk is one contiguous 16 KB block
 //   training cache : per 128-row tile 40 activation blocks, then per tile 69 x 128 ReLU-mask words
 //   bwd scratch    : per tile 38 gradient blocks, then per row float4 {gz0, gz1, gz2, g_sigma_pre}
+//
+// Cache and scratch tiles are stored SLICE-MAJOR: the tile is four 32-row slices, each slice holds the 4 KB
+// (32 rows x 128 B) piece of every block back to back.  The chain epilogues write 4 KB pieces anyway, and wgrad
+// fetches the pieces of several consecutive blocks of one slice with a single bulk copy.
 #pragma once
 
 #include <stddef.h>
@@ -65,6 +69,10 @@ constexpr int kCacheDe = 37;                                 // encoded view dir
 constexpr int kCacheH9 = 38;                                 // fc_9 output (128 columns), 2 blocks
 constexpr int kCacheBlocks = 40;
 constexpr size_t kCacheTileBytes = (size_t)kCacheBlocks * kBlockBytes;
+constexpr int kSliceBytes = 4096;  // 32 rows x 128 B of one block
+// byte offset inside a tile of rows [32 q, 32 q + 32) of block `blk` (`nblk` = blocks per tile)
+__host__ __device__ constexpr size_t slice_off(int nblk, int blk, int q) { return ((size_t)q * nblk + blk) * kSliceBytes; }
+__host__ __device__ constexpr size_t cache_slice_off(int blk, int q) { return ((size_t)q * kCacheBlocks + blk) * kSliceBytes; }
 // ReLU masks: word (slot s, 32-column group c) of row r at ((s*8 + c)*128 + r); slots 0..7 = h0..h7, slot 8 = h9
 // (4 words).  Bit (31 - i) of a word is the SIGN BIT of the pre-activation of column 32c + i (1 = negative = no
 // gradient), collected with one funnel shift per element.  Word 68 bit 0 = (sigma_pre > 0).
@@ -82,6 +90,7 @@ constexpr int kGradG8 = 2;                                   // feature part of 
 __host__ __device__ constexpr int grad_g(int l) { return 6 + 4 * (7 - l); }  // G_l for l = 7..0
 constexpr int kGradBlocks = 38;
 constexpr size_t kGradTileBytes = (size_t)kGradBlocks * kBlockBytes;
+__host__ __device__ constexpr size_t grad_slice_off(int blk, int q) { return ((size_t)q * kGradBlocks + blk) * kSliceBytes; }
 // head gradients per row as float4 {gz0, gz1, gz2, g_sigma_pre} (gz = dL/d(fc_out pre-sigmoid))
 __host__ __device__ inline size_t scratch_ghead_offset(int64_t m) { return (size_t)num_tiles(m) * kGradTileBytes; }
 __host__ __device__ inline size_t scratch_bytes(int64_t m) { return scratch_ghead_offset(m) + (size_t)num_tiles(m) * kTileM * 16; }
