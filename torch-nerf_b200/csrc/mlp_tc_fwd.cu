@@ -139,6 +139,46 @@ __device__ __forceinline__ uint32_t finish_group(const uint32_t (&v)[32], const 
   return neg;
 }
 
+// two fp32 adds in one instruction (FADD2 on sm_100)
+__device__ __forceinline__ void add2(float a0, float a1, float b0, float b1, float& o0, float& o1) {
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(o0), "=f"(o1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+// two fp32 -> packed bf16 pair (lo in the low half), ReLU folded into the conversion
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+  uint32_t w;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(hi), "f"(lo));
+  return w;
+}
+
+// 32 accumulator columns -> +bias -> (ReLU) -> 16 packed bf16 pairs, without materialising the fp32 activations:
+// FADD2 for the bias, the ReLU rides on the bf16 conversion.  Returns the sign bits like finish_group when MASK.
+template <bool RELU, bool MASK>
+__device__ __forceinline__ uint32_t finish_pack(const uint32_t (&v)[32], const float* __restrict__ bias, uint32_t (&w)[16]) {
+  uint32_t neg = 0;
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + i);
+    float t0, t1, t2, t3;
+    add2(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), b.x, b.y, t0, t1);
+    add2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]), b.z, b.w, t2, t3);
+    if (RELU && MASK) {
+      neg = __funnelshift_l(__float_as_uint(t0), neg, 1);
+      neg = __funnelshift_l(__float_as_uint(t1), neg, 1);
+      neg = __funnelshift_l(__float_as_uint(t2), neg, 1);
+      neg = __funnelshift_l(__float_as_uint(t3), neg, 1);
+    }
+    w[i / 2] = RELU ? pack_bf16_relu(t0, t1) : pack_bf16(t0, t1);
+    w[i / 2 + 1] = RELU ? pack_bf16_relu(t2, t3) : pack_bf16(t2, t3);
+  }
+  return neg;
+}
+
 // 32 fp32 values -> 16 packed bf16 pairs
 __device__ __forceinline__ void pack_group(const float (&f)[32], uint32_t (&w)[16]) {
 #pragma unroll
@@ -407,12 +447,22 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
               tc_fence_before();
               mbar_arrive(&acc_free[s]);
             }
-            float f[32];
             uint32_t w[16];
             uint32_t neg;
-            if (l == 8) neg = finish_group<false>(v, bias + col0, f);
-            else neg = finish_group<true>(v, bias + col0, f);
-            pack_group(f, w);
+            if (l == 7) {
+              // the density head (fc_8 row 0) is an fp32 dot product with the fp32 activations
+              float f[32];
+              neg = finish_group<true>(v, bias + col0, f);
+              pack_group(f, w);
+              float acc_s = sigma_part[s];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) acc_s = fmaf(f[i], sC[kCW8Row0 + col0 + i], acc_s);
+              sigma_part[s] = acc_s;
+            } else if (l == 8) {
+              neg = finish_pack<false, false>(v, bias + col0, w);
+            } else {
+              neg = finish_pack<true, kTrain>(v, bias + col0, w);
+            }
             if (h == 0) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) wh[s][j] = w[j];
@@ -422,12 +472,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
               tmem_st_wait();
               tc_fence_before();
               mbar_arrive(&a_ready[s]);
-            }
-            if (l == 7) {
-              float acc_s = sigma_part[s];
-#pragma unroll
-              for (int i = 0; i < 32; ++i) acc_s = fmaf(f[i], sC[kCW8Row0 + col0 + i], acc_s);
-              sigma_part[s] = acc_s;
             }
             if (kTrain && tile0 + s < ntiles) {
               // layer input of the backward pass as a tile image + the ReLU sign bits
