@@ -206,6 +206,11 @@ int nerf_debug_set_wgrad_profile(unsigned long long* buf_dev);
 int nerf_selftest_mma_rate(int blocks, int iters, int n, int mode, int bg_warps, int bg_iters, int bg_store,
                            unsigned long long* cycles_dev, nerf_stream_t stream);
 
+/* micro-benchmark: `blocks` CTAs stream `bytes` (multiple of 4096) to dst_dev in 4 KB pieces.  mode 0: st.global.v4,
+ * 1: st.global.cs.v4, 2: bulk stores (TMA engine) from shared memory, 3 / 4: bulk stores with an L2 evict_first /
+ * evict_last cache hint.  Used to find the HBM write ceiling the training-cache stores run against. */
+int nerf_selftest_write_bw(void* dst_dev, size_t bytes, int mode, int blocks, nerf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

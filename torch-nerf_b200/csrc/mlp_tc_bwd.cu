@@ -27,7 +27,7 @@ using namespace tc;
 // ================================================================================================
 // 1. dgrad chain
 // ================================================================================================
-constexpr int kDgStages = 10;                    // 16 KB weight chunks (128 input features x 64 output features)
+constexpr int kDgStages = 9;                     // 16 KB weight chunks (128 input features x 64 output features)
 constexpr int kDgEpiWarps = 16;
 constexpr int kDgEpiThreads = kDgEpiWarps * 32;
 constexpr int kDgMmaWarpB = 2 + kDgEpiWarps;
@@ -35,8 +35,8 @@ constexpr int kDgThreads = 32 * (3 + kDgEpiWarps);  // loader, MMA issuer X, 16 
 // shared memory map
 constexpr int kDgSmC = 0;                        // w8row0 (256) | wout (384)
 constexpr int kDgSmBar = kDgSmC + 640 * 4;
-constexpr int kDgSmStage = 4096;                 // 8 warp pairs x 4 KB staging slices for the bulk stores
-constexpr int kDgSmW = kDgSmStage + 32768;       // weight ring
+constexpr int kDgSmStage = 4096;                 // 16 warps x 4 KB staging slices for the bulk stores
+constexpr int kDgSmW = kDgSmStage + 65536;       // weight ring
 constexpr int kDgSmTotal = kDgSmW + kDgStages * kChunkBytes;
 constexpr int kDgSmemBytes = kDgSmTotal + 1024;
 static_assert(kDgSmemBytes <= 232448, "shared memory budget");
@@ -107,8 +107,8 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
       mbar_init(&empty[i], 2);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_ready[i], kDgEpiThreads);
-      mbar_init(&acc_free[i], kDgEpiThreads);
+      mbar_init(&a_ready[i], kDgEpiThreads / 2);   // the slot's eight epilogue warps
+      mbar_init(&acc_free[i], kDgEpiThreads / 2);
       mbar_init(&acc_full[i], 1);
     }
     fence_barrier_init();
@@ -179,62 +179,55 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
       }
     }
   } else {
-    // 16 epilogue warps = 4 per TMEM lane quarter; per event (slot, N-half h) column group cg owns accumulator
-    // columns [32 cg, +32) = gradient columns [128 h + 32 cg, +32)
+    // 16 epilogue warps = 4 per TMEM lane quarter, two serving slot X and two slot Y; a warp owns 32 rows x the 64
+    // columns [64 blk, +64) of each N-half of its slot = one whole gradient block row (128 B): private 4 KB staging
+    // slice, one bulk store per event (see mlp_tc_fwd.cu)
     const int q = warp & 3;
-    const int cg = (warp - 2) >> 2;
+    const int e = (warp - 2) >> 2;
+    const int slot = e >> 1, blk = e & 1;
     const int row = q * 32 + lane;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    // warps (cg, cg^1) of one quarter share a 32-row x 128 B staging slice and a named barrier; the slice
-    // leaves through the TMA engine (one 4 KB bulk store), which unlike st.global (32 B/clk/SM through the LSU,
-    // measured) does not hold up the epilogue warps
-    const int pair_id = q * 2 + (cg >> 1);
-    uint8_t* st_slice = sStage + pair_id * 4096;
-    const bool pair_leader = ((cg & 1) == 0) && lane == 0;
-    uint32_t n_full[2] = {0, 0};
+    const uint32_t t_slot = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)slot * kDgTmSlot;
+    uint8_t* st_row = sStage + (warp - 2) * 4096 + lane * 128;
+    uint32_t n_full = 0;
     float4* ghead_out = reinterpret_cast<float4*>(a.scratch + scratch_ghead_offset(a.m));
 
-    // this warp pair's 32 rows of one 64-column block -> HBM; `gdst` = the block's rows [32 q, 32 q + 32)
-    auto stage_store = [&](const uint32_t (&w)[16], uint8_t* gdst) {
-      if (pair_leader) bulk_wait_read<0>();  // the previous store out of the slice has been read
-      __syncwarp();
-      named_bar_sync(2 + pair_id, 64);
-      store_words(w, st_slice + lane * 128, row, 4 * (cg & 1));
+    auto bulk_out = [&](uint8_t* gdst) {  // the staged 32 rows x 128 B -> HBM
       fence_proxy_async();
-      named_bar_sync(2 + pair_id, 64);
-      if (pair_leader) {
-        bulk_s2g(gdst, st_slice, 4096);
+      __syncwarp();
+      if (lane == 0) {
+        bulk_s2g(gdst, st_row, 4096);  // lane 0: st_row = start of the slice
         bulk_commit();
       }
+    };
+    auto staging_free = [&]() {
+      if (lane == 0) bulk_wait_read<0>();  // the previous store out of the slice has been read
       __syncwarp();
     };
 
     for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-      const int64_t tile0 = 2 * pair;
-      float gsp[2];
-      // ---- input stage per slot: heads on CUDA cores, G9 into TMEM
+      const int64_t tile = 2 * pair + slot;
+      const bool valid = tile < ntiles;
+      const int64_t grow = tile * kTileM + row;
+      uint8_t* g_tile = a.scratch + (size_t)tile * kGradTileBytes;
+      const uint32_t* mask_row =
+          reinterpret_cast<const uint32_t*>(a.cache + cache_mask_offset(a.m) + (size_t)tile * kMaskTileBytes) + row;
+      // ---- input stage: heads on CUDA cores: gz = g_rgb * rgb (1 - rgb) (sigmoid backward),
+      //      g_sigma_pre = g_sigma * (sigma_pre > 0); G9 = (gz . W_out) masked by h9 > 0 into TMEM
+      float gz0 = 0.f, gz1 = 0.f, gz2 = 0.f, gsp = 0.f;
+      if (grow < a.m) {
+        const float r0 = __ldg(a.rgb + 3 * grow), r1 = __ldg(a.rgb + 3 * grow + 1), r2 = __ldg(a.rgb + 3 * grow + 2);
+        gz0 = __ldg(a.g_rgb + 3 * grow) * r0 * (1.f - r0);
+        gz1 = __ldg(a.g_rgb + 3 * grow + 1) * r1 * (1.f - r1);
+        gz2 = __ldg(a.g_rgb + 3 * grow + 2) * r2 * (1.f - r2);
+        const uint32_t smask = __ldg(mask_row + kMaskSigmaWord * kTileM);
+        gsp = (smask & 1u) ? __ldg(a.g_sigma + grow) : 0.f;
+      }
+      if (blk == 0 && valid) ghead_out[tile * kTileM + row] = make_float4(gz0, gz1, gz2, gsp);
+      staging_free();
 #pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        const int64_t tile = tile0 + s;
-        const bool valid = tile < ntiles;
-        const int64_t grow = tile * kTileM + row;
-        const uint32_t* mask_row =
-            reinterpret_cast<const uint32_t*>(a.cache + cache_mask_offset(a.m) + (size_t)tile * kMaskTileBytes) + row;
-        // gz = g_rgb * rgb (1 - rgb) (sigmoid backward), g_sigma_pre = g_sigma * (sigma_pre > 0)
-        float gz0 = 0.f, gz1 = 0.f, gz2 = 0.f;
-        gsp[s] = 0.f;
-        if (grow < a.m) {
-          const float r0 = __ldg(a.rgb + 3 * grow), r1 = __ldg(a.rgb + 3 * grow + 1), r2 = __ldg(a.rgb + 3 * grow + 2);
-          gz0 = __ldg(a.g_rgb + 3 * grow) * r0 * (1.f - r0);
-          gz1 = __ldg(a.g_rgb + 3 * grow + 1) * r1 * (1.f - r1);
-          gz2 = __ldg(a.g_rgb + 3 * grow + 2) * r2 * (1.f - r2);
-          const uint32_t smask = __ldg(mask_row + kMaskSigmaWord * kTileM);
-          gsp[s] = (smask & 1u) ? __ldg(a.g_sigma + grow) : 0.f;
-        }
-        if (cg == 0 && valid) ghead_out[tile * kTileM + row] = make_float4(gz0, gz1, gz2, gsp[s]);
-        // G9 = (gz . W_out) masked by h9 > 0; this thread owns columns [32 cg, 32 cg + 32)
-        const int col0 = 32 * cg;
-        const uint32_t mk = valid ? __ldg(mask_row + (64 + cg) * kTileM) : 0u;
+      for (int gi = 0; gi < 2; ++gi) {
+        const int col0 = 64 * blk + 32 * gi;
+        const uint32_t mk = valid ? __ldg(mask_row + (64 + 2 * blk + gi) * kTileM) : 0u;
         float f[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -245,57 +238,81 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
         }
         uint32_t w[16];
         pack_words(f, w);
-        tmem_st16(lane_addr + (uint32_t)s * kDgTmSlot + kDgTmA + 16 * cg, w);
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&a_ready[s]);  // also: this thread has drained the slot's previous tile
-        if (valid) stage_store(w, a.scratch + (size_t)tile * kGradTileBytes + grad_slice_off(kGradG9 + (cg >> 1), q));
+        tmem_st16(t_slot + kDgTmA + 32 * blk + 16 * gi, w);  // layer 0 reads k-blocks 0, 1
+        if (valid) store_words(w, st_row, row, 4 * gi);
       }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&a_ready[slot]);  // also: this thread has drained the slot's previous tile
+      if (valid) bulk_out(g_tile + grad_slice_off(kGradG9 + blk, q));
+
       uint32_t wh[2][16];  // bf16 pairs of N-half 0, held until half 1's MMAs have stopped reading the G operand
 #pragma unroll 1
       for (int j = 0; j < kNumBwdLayers; ++j) {
         const int slot_m = 8 - j;  // ReLU mask of the layer output this gradient flows into (j >= 1): h7 .. h0
+        // sign-bit masks of this thread's four 32-column groups (0 = every column passes: layer j = 0 has no ReLU)
+        uint32_t mk[4] = {0u, 0u, 0u, 0u};
+        if (j >= 1 && valid) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            const int64_t tile = tile0 + s;
-            const bool valid = tile < ntiles;
-            const int col0 = 128 * h + 32 * cg;
-            const uint32_t t_slot = lane_addr + (uint32_t)s * kDgTmSlot;
-            uint32_t mk = 0u;  // sign-bit mask: 0 = every column passes (layer j = 0 has no ReLU)
-            if (j >= 1 && valid)
-              mk = __ldg(reinterpret_cast<const uint32_t*>(a.cache + cache_mask_offset(a.m) + (size_t)tile * kMaskTileBytes) +
-                         row + (slot_m * 8 + 4 * h + cg) * kTileM);
-            mbar_wait(&acc_full[s], n_full[s] & 1);
-            ++n_full[s];
-            tc_fence_after();
-            uint32_t v[32];
-            tmem_ld32(t_slot + 32 * cg, v);
-            tmem_ld_wait();
-            if (h == 0) {
-              tc_fence_before();
-              mbar_arrive(&acc_free[s]);
-            }
-            float f[32];
-            uint32_t w[16];
-            masked_group(v, mk, gsp[s], j == 1 ? sW8 + col0 : nullptr, f);
-            pack_words(f, w);
-            if (h == 0) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) wh[s][i] = w[i];
-            } else if (j < kNumBwdLayers - 1) {
-              tmem_st16(t_slot + kDgTmA + 16 * cg, wh[s]);
-              tmem_st16(t_slot + kDgTmA + 64 + 16 * cg, w);
-              tmem_st_wait();
-              tc_fence_before();
-              mbar_arrive(&a_ready[s]);
-            } else {
-              tc_fence_before();
-            }
-            // gradient block for wgrad
-            if (valid)
-              stage_store(w, a.scratch + (size_t)tile * kGradTileBytes + grad_slice_off(2 + 4 * j + 2 * h + (cg >> 1), q));
+          for (int i = 0; i < 4; ++i) mk[i] = __ldg(mask_row + (slot_m * 8 + 4 * (i >> 1) + 2 * blk + (i & 1)) * kTileM);
+        }
+        auto finish = [&](const uint32_t (&v)[32], uint32_t m, int col0, uint32_t (&w)[16]) {
+          float f[32];
+          masked_group(v, m, gsp, j == 1 ? sW8 + col0 : nullptr, f);
+          pack_words(f, w);
+        };
+        uint8_t* gblk0 = g_tile + grad_slice_off(2 + 4 * j + blk, q);  // gradient block of N-half 0's columns
+        // ---- N-half 0: pull it out of the accumulator first (the issuer is waiting for that), then convert and hold it
+        {
+          mbar_wait(&acc_full[slot], n_full & 1);
+          ++n_full;
+          tc_fence_after();
+          uint32_t v0[32], v1[32];
+          tmem_ld32(t_slot + 64 * blk, v0);
+          tmem_ld32(t_slot + 64 * blk + 32, v1);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(&acc_free[slot]);
+          finish(v0, mk[0], 64 * blk, wh[0]);
+          finish(v1, mk[1], 64 * blk + 32, wh[1]);
+          if (valid) {
+            staging_free();
+            store_words(wh[0], st_row, row, 0);
+            store_words(wh[1], st_row, row, 4);
+            bulk_out(gblk0);
+          }
+        }
+        // ---- N-half 1: once complete nothing reads the G operand any more -> overwrite it in place, signal the
+        //      issuer, then store the gradient block for wgrad
+        {
+          mbar_wait(&acc_full[slot], n_full & 1);
+          ++n_full;
+          tc_fence_after();
+          uint32_t v[32], w0[16], w1[16];
+          tmem_ld32(t_slot + 64 * blk, v);
+          tmem_ld_wait();
+          finish(v, mk[2], 128 + 64 * blk, w0);
+          if (j < kNumBwdLayers - 1) {
+            tmem_st16(t_slot + kDgTmA + 32 * blk, wh[0]);
+            tmem_st16(t_slot + kDgTmA + 64 + 32 * blk, w0);
+          }
+          tmem_ld32(t_slot + 64 * blk + 32, v);
+          tmem_ld_wait();
+          finish(v, mk[3], 128 + 64 * blk + 32, w1);
+          if (j < kNumBwdLayers - 1) {
+            tmem_st16(t_slot + kDgTmA + 32 * blk + 16, wh[1]);
+            tmem_st16(t_slot + kDgTmA + 64 + 32 * blk + 16, w1);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&a_ready[slot]);
+          } else {
+            tc_fence_before();
+          }
+          if (valid) {
+            staging_free();
+            store_words(w0, st_row, row, 0);
+            store_words(w1, st_row, row, 4);
+            bulk_out(gblk0 + 2 * kSliceBytes);  // block + 2 of the same slice
           }
         }
       }

@@ -40,25 +40,26 @@
 namespace nerf {
 using namespace tc;
 
-constexpr int kMaxStages = 9;
+constexpr int kMaxStages = 10;
 template <bool kTrain>
 struct FwdCfg {
-  static constexpr int kStages = kTrain ? 7 : 9;  // inference uses the staging area as two more weight stages
+  static constexpr int kStages = kTrain ? 6 : 10;  // inference uses the staging area as four more weight stages
 };
 constexpr int kEpiWarps = 16;
-constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kSlotThreads = kEpiWarps * 32 / 2;   // epilogue threads serving one tile slot
 constexpr int kMmaWarpB = 2 + kEpiWarps;
 constexpr int kFwdThreads = 32 * (3 + kEpiWarps);  // loader, MMA issuer X, 16 epilogue warps, MMA issuer Y
 // shared memory map (bytes from the 1024-aligned base)
 constexpr int kSmIn = 0;                        // pe block slot X | pe block slot Y | de block (X: chunks 0-3, Y: chunks 4-7)
 constexpr int kSmC = 3 * kBlockBytes;           // fp32 constants
-constexpr int kSmX = kSmC + kCFloats * 4;       // 2 slots x 128 rows x 4 column groups x {rgb0, rgb1, rgb2, sigma} partial sums
-constexpr int kSmBar = kSmX + 2 * 128 * 64;
-constexpr int kSmStage = (kSmBar + 512 + 1023) / 1024 * 1024;  // training: 8 warp pairs x 4 KB staging slices
-constexpr int kSmWTrain = kSmStage + 32768;     // weight ring (training)
+constexpr int kSmX = kSmC + kCFloats * 4;       // 2 slots x 128 rows x {rgb0, rgb1, rgb2, sigma} partial sums of block 1
+constexpr int kSmBar = kSmX + 2 * 128 * 16;
+constexpr int kSmStage = (kSmBar + 512 + 1023) / 1024 * 1024;  // training: 16 warps x 4 KB staging slices
+constexpr int kSmWTrain = kSmStage + 65536;     // weight ring (training)
 constexpr int kSmWInfer = kSmStage;             // weight ring (inference)
 constexpr int kSmTotal = kSmStage + kMaxStages * kChunkBytes;
 constexpr int kFwdSmemBytes = kSmTotal + 1024;  // + alignment slack
+static_assert(kSmWTrain + 6 * kChunkBytes <= kSmTotal, "training ring fits");
 static_assert(kFwdSmemBytes <= 232448, "shared memory budget");
 // tensor memory map (columns), per slot
 constexpr uint32_t kTmSlot = 256;
@@ -226,9 +227,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
       mbar_init(&empty[i], 2);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&in_ready[i], kEpiThreads);
-      mbar_init(&a_ready[i], kEpiThreads);
-      mbar_init(&acc_free[i], kEpiThreads);
+      mbar_init(&in_ready[i], kSlotThreads);
+      mbar_init(&a_ready[i], kSlotThreads);
+      mbar_init(&acc_free[i], kSlotThreads);
       mbar_init(&acc_full[i], 1);
     }
     fence_barrier_init();
@@ -342,45 +343,44 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    // 16 warps = 4 per TMEM lane quarter; per event (slot, N-half h) column group cg owns accumulator columns
-    // [32 cg, +32) = layer output columns [128 h + 32 cg, +32) = half of k-block (2 h + cg/2) of the next layer.
+    // 16 warps = 4 per TMEM lane quarter; two of them serve tile slot X and two slot Y.  A warp owns 32 rows x the
+    // 64 columns [64 blk, +64) of each N-half of its slot's accumulator = one whole k-block (128-byte row) of the next
+    // layer's operand, so its training-cache store needs nobody else: private 4 KB staging slice, one bulk store.
     const int q = warp & 3;             // TMEM lane quarter this warp may access
-    const int cg = (warp - 2) >> 2;     // column group 0..3
+    const int e = (warp - 2) >> 2;
+    const int slot = e >> 1;            // tile slot served by this warp
+    const int blk = e & 1;              // which 64-column block of an N-half
     const int row = q * 32 + lane;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    // training: warps (cg, cg^1) of one quarter share a 32-row x 128 B staging slice and a named barrier; the slice
-    // leaves through the TMA engine (one 4 KB bulk store), which unlike st.global (32 B/clk/SM through the LSU,
-    // measured) does not hold up the epilogue warps
-    const int pair_id = q * 2 + (cg >> 1);
-    uint8_t* st_slice = sStage + pair_id * 4096;
-    const bool pair_leader = ((cg & 1) == 0) && lane == 0;
-    uint32_t n_full[2] = {0, 0};
+    const uint32_t t_slot = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)slot * kTmSlot;
+    uint8_t* st_row = sStage + (warp - 2) * 4096 + lane * 128;
+    uint32_t n_full = 0;
     int iter = 0;
 
-    // this warp pair's 32 rows of one 64-column block -> HBM; `gdst` = the block's rows [32 q, 32 q + 32)
-    auto stage_store = [&](const uint32_t (&w)[16], uint8_t* gdst) {
-      if (pair_leader) bulk_wait_read<0>();  // the previous store out of the slice has been read
-      __syncwarp();
-      named_bar_sync(2 + pair_id, 64);
-      store_words(w, st_slice + lane * 128, row, 4 * (cg & 1));
+    // the staged 32 rows x 128 B -> HBM; `gdst` = rows [32 q, 32 q + 32) of one block
+    auto bulk_out = [&](uint8_t* gdst) {
       fence_proxy_async();
-      named_bar_sync(2 + pair_id, 64);
-      if (pair_leader) {
-        bulk_s2g(gdst, st_slice, 4096);
+      __syncwarp();
+      if (lane == 0) {
+        bulk_s2g(gdst, st_row, 4096);  // lane 0: st_row = start of the slice
         bulk_commit();
       }
+    };
+    auto staging_free = [&]() {
+      if (lane == 0) bulk_wait_read<0>();  // the previous store out of the slice has been read
       __syncwarp();
     };
 
     for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++iter) {
       const bool stamp = a.prof != nullptr && blockIdx.x == 0 && iter < a.prof_tiles && warp == 2 && lane == 0;
-      const int64_t tile0 = 2 * pair;
-      // ---- encoded inputs (cube.py:62-69): groups 0/1 encode the points of slots X/Y, groups 2/3 the view directions
+      const int64_t tile = 2 * pair + slot;
+      const int64_t grow = tile * kTileM + row;
+      const bool to_cache = kTrain && tile < ntiles;
+      uint8_t* cache_tile = kTrain ? a.cache + (size_t)tile * kCacheTileBytes : nullptr;
+      uint32_t* mask_row =
+          kTrain ? reinterpret_cast<uint32_t*>(a.cache + cache_mask_offset(a.m) + (size_t)tile * kMaskTileBytes) + row : nullptr;
+      // ---- encoded inputs (cube.py:62-69): block 0 warps encode the point, block 1 warps the view direction
       {
-        const int s_in = cg & 1;
-        const bool is_pe = cg < 2;
-        const int64_t tile = tile0 + s_in;
-        const int64_t grow = tile * kTileM + row;
+        const bool is_pe = blk == 0;
         float x = 0.f, y = 0.f, z = 0.f;
         if (grow < a.m) {
           if (a.pts != nullptr) {
@@ -398,147 +398,151 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
             }
           }
         }
-        const bool to_cache = kTrain && tile < ntiles;
-        uint8_t* cache_tile_in = kTrain ? a.cache + (size_t)tile * kCacheTileBytes : nullptr;
         if (is_pe) {
-          if (kTrain) {
-            if (lane == 0) bulk_wait_read<0>();  // the previous pair's store out of this pe block has been read
-            __syncwarp();
-          }
-          encode_row<10, 8, false>(x, y, z, sIn + s_in * kBlockBytes + row * 128, 0, nullptr, row);
+          if (kTrain) staging_free();  // also covers the previous pair's store out of the pe block (same thread's groups)
+          encode_row<10, 8, false>(x, y, z, sIn + slot * kBlockBytes + row * 128, 0, nullptr, row);
           fence_proxy_async();
           if (kTrain) {
             __syncwarp();
             if (lane == 0 && to_cache) {
-              bulk_s2g(cache_tile_in + cache_slice_off(kCachePe, q), sIn + s_in * kBlockBytes + q * 4096, 4096);
+              bulk_s2g(cache_tile + cache_slice_off(kCachePe, q), sIn + slot * kBlockBytes + q * 4096, 4096);
               bulk_commit();
             }
           }
         } else {
           if (to_cache)
-            encode_row<4, 4, true>(x, y, z, sIn + 2 * kBlockBytes + row * 128, 4 * s_in,
-                                   cache_tile_in + cache_slice_off(kCacheDe, q) + lane * 128, row);
+            encode_row<4, 4, true>(x, y, z, sIn + 2 * kBlockBytes + row * 128, 4 * slot,
+                                   cache_tile + cache_slice_off(kCacheDe, q) + lane * 128, row);
           else
-            encode_row<4, 4, false>(x, y, z, sIn + 2 * kBlockBytes + row * 128, 4 * s_in, nullptr, row);
+            encode_row<4, 4, false>(x, y, z, sIn + 2 * kBlockBytes + row * 128, 4 * slot, nullptr, row);
           fence_proxy_async();
         }
-        mbar_arrive(&in_ready[0]);  // all 512 threads on both: inputs written AND this thread has left the previous pair
-        mbar_arrive(&in_ready[1]);
+        mbar_arrive(&in_ready[slot]);  // inputs written AND this thread has left the slot's previous tile
       }
-      float sigma_part[2] = {0.f, 0.f};
+      float sigma_part = 0.f;
       uint32_t wh[2][16];  // bf16 pairs of N-half 0, held until half 1's MMAs have stopped reading the layer input
 #pragma unroll 1
       for (int l = 0; l < kNumFwdLayers - 1; ++l) {
         const float* bias = sC + ((l < 8) ? kCBias + 256 * l : kCBias8);
+        // one 32-column group: accumulator values -> bf16 pairs `w` (+ ReLU sign bits); layer 7 also feeds the density head
+        auto finish = [&](const uint32_t (&v)[32], int col0, uint32_t (&w)[16]) -> uint32_t {
+          if (l == 7) {
+            // the density head (fc_8 row 0) is an fp32 dot product with the fp32 activations
+            float f[32];
+            const uint32_t neg = finish_group<true>(v, bias + col0, f);
+            pack_group(f, w);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            const int col0 = 128 * h + 32 * cg;
-            const uint32_t t_slot = lane_addr + (uint32_t)s * kTmSlot;
-            mbar_wait(&acc_full[s], n_full[s] & 1);
-            ++n_full[s];
-            tc_fence_after();
-            if (stamp && s == 0 && h == 0) a.prof[((iter * kNumFwdLayers + l) * 8) + 2] = clock64();
-            uint32_t v[32];
-            tmem_ld32(t_slot + 32 * cg, v);
-            tmem_ld_wait();
-            if (h == 0) {
-              tc_fence_before();
-              mbar_arrive(&acc_free[s]);
-            }
-            uint32_t w[16];
-            uint32_t neg;
-            if (l == 7) {
-              // the density head (fc_8 row 0) is an fp32 dot product with the fp32 activations
-              float f[32];
-              neg = finish_group<true>(v, bias + col0, f);
-              pack_group(f, w);
-              float acc_s = sigma_part[s];
-#pragma unroll
-              for (int i = 0; i < 32; ++i) acc_s = fmaf(f[i], sC[kCW8Row0 + col0 + i], acc_s);
-              sigma_part[s] = acc_s;
-            } else if (l == 8) {
-              neg = finish_pack<false, false>(v, bias + col0, w);
-            } else {
-              neg = finish_pack<true, kTrain>(v, bias + col0, w);
-            }
-            if (h == 0) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) wh[s][j] = w[j];
-            } else {
-              tmem_st16(t_slot + kTmA + 16 * cg, wh[s]);       // output columns [32 cg, +32)
-              tmem_st16(t_slot + kTmA + 64 + 16 * cg, w);      // output columns [128 + 32 cg, +32)
-              tmem_st_wait();
-              tc_fence_before();
-              mbar_arrive(&a_ready[s]);
-            }
-            if (kTrain && tile0 + s < ntiles) {
-              // layer input of the backward pass as a tile image + the ReLU sign bits
-              uint8_t* cache_tile = a.cache + (size_t)(a.dbg_store == 2 ? (int64_t)(2 * blockIdx.x + s) : (tile0 + s)) * kCacheTileBytes;
-              if (l < 8) {
-                uint32_t* mask_row = reinterpret_cast<uint32_t*>(a.cache + cache_mask_offset(a.m) +
-                                                                 (size_t)(tile0 + s) * kMaskTileBytes) + row;
-                mask_row[(l * 8 + 4 * h + cg) * kTileM] = neg;
-              }
-              int blk = (l < 8 ? cache_h(l) : kCacheFeat) + 2 * h + (cg >> 1);
-              if (a.dbg_store == 2) blk &= 3;  // debug: every CTA rewrites its own 128 KB window (L2 resident)
-              if (a.dbg_store != 1) stage_store(w, cache_tile + cache_slice_off(blk, q));
-            }
-            if (stamp && s == 0 && h == 1) a.prof[((iter * kNumFwdLayers + l) * 8) + 3] = clock64();
+            for (int i = 0; i < 32; ++i) sigma_part = fmaf(f[i], sC[kCW8Row0 + col0 + i], sigma_part);
+            return neg;
           }
+          if (l == 8) return finish_pack<false, false>(v, bias + col0, w);
+          return finish_pack<true, kTrain>(v, bias + col0, w);
+        };
+        const int cblk0 = (l < 8 ? cache_h(l) : kCacheFeat) + blk;  // cache block of N-half 0's columns
+        // ---- N-half 0: pull it out of the accumulator first (the issuer is waiting for that), then convert and hold it
+        {
+          mbar_wait(&acc_full[slot], n_full & 1);
+          ++n_full;
+          tc_fence_after();
+          if (stamp) a.prof[((iter * kNumFwdLayers + l) * 8) + 2] = clock64();
+          uint32_t v0[32], v1[32];
+          tmem_ld32(t_slot + 64 * blk, v0);
+          tmem_ld32(t_slot + 64 * blk + 32, v1);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(&acc_free[slot]);
+          const uint32_t neg0 = finish(v0, 64 * blk, wh[0]);
+          const uint32_t neg1 = finish(v1, 64 * blk + 32, wh[1]);
+          if (to_cache) {
+            staging_free();
+            if (l < 8) {
+              mask_row[(l * 8 + 2 * blk) * kTileM] = neg0;
+              mask_row[(l * 8 + 2 * blk + 1) * kTileM] = neg1;
+            }
+            store_words(wh[0], st_row, row, 0);
+            store_words(wh[1], st_row, row, 4);
+            if (a.dbg_store != 1) bulk_out(cache_tile + cache_slice_off(cblk0, q));
+          }
+        }
+        // ---- N-half 1: once it is complete nothing reads the layer input any more -> overwrite it in place, signal
+        //      the issuer, and only then do the training-cache stores
+        {
+          mbar_wait(&acc_full[slot], n_full & 1);
+          ++n_full;
+          tc_fence_after();
+          uint32_t v[32], w0[16], w1[16];
+          tmem_ld32(t_slot + 64 * blk, v);
+          tmem_ld_wait();
+          const uint32_t neg0 = finish(v, 128 + 64 * blk, w0);
+          tmem_st16(t_slot + kTmA + 32 * blk, wh[0]);            // output columns [64 blk, +32)
+          tmem_st16(t_slot + kTmA + 64 + 32 * blk, w0);          // output columns [128 + 64 blk, +32)
+          tmem_ld32(t_slot + 64 * blk + 32, v);
+          tmem_ld_wait();
+          const uint32_t neg1 = finish(v, 128 + 64 * blk + 32, w1);
+          tmem_st16(t_slot + kTmA + 32 * blk + 16, wh[1]);
+          tmem_st16(t_slot + kTmA + 64 + 32 * blk + 16, w1);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&a_ready[slot]);
+          if (to_cache) {
+            staging_free();
+            if (l < 8) {
+              mask_row[(l * 8 + 4 + 2 * blk) * kTileM] = neg0;
+              mask_row[(l * 8 + 4 + 2 * blk + 1) * kTileM] = neg1;
+            }
+            store_words(w0, st_row, row, 0);
+            store_words(w1, st_row, row, 4);
+            if (a.dbg_store != 1) bulk_out(cache_tile + cache_slice_off(cblk0 + 2, q));
+          }
+          if (stamp) a.prof[((iter * kNumFwdLayers + l) * 8) + 3] = clock64();
         }
       }
-      // ---- fc_9 output (128 columns = one N-half): this thread owns columns [32 cg, 32 cg + 32)
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
+      // ---- fc_9 output (128 columns = one N-half): this warp owns columns [64 blk, 64 blk + 64)
+      {
         const int l = kNumFwdLayers - 1;
-        const int col0 = 32 * cg;
-        const int64_t tile = tile0 + s;
-        const int64_t grow = tile * kTileM + row;
-        mbar_wait(&acc_full[s], n_full[s] & 1);
-        ++n_full[s];
+        mbar_wait(&acc_full[slot], n_full & 1);
+        ++n_full;
         tc_fence_after();
-        if (stamp && s == 0) a.prof[((iter * kNumFwdLayers + l) * 8) + 2] = clock64();
-        uint32_t v[32];
-        tmem_ld32(lane_addr + (uint32_t)s * kTmSlot + col0, v);
-        tmem_ld_wait();
-        tc_fence_before();
-        float f[32];
-        const uint32_t neg = finish_group<true>(v, sC + kCBias9 + col0, f);
+        if (stamp) a.prof[((iter * kNumFwdLayers + l) * 8) + 2] = clock64();
+        if (kTrain) staging_free();
         float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          rgb0 = fmaf(f[i], sC[kCWout + col0 + i], rgb0);
-          rgb1 = fmaf(f[i], sC[kCWout + 128 + col0 + i], rgb1);
-          rgb2 = fmaf(f[i], sC[kCWout + 256 + col0 + i], rgb2);
-        }
-        if (cg != 0) sX[(s * 128 + row) * 4 + cg] = make_float4(rgb0, rgb1, rgb2, sigma_part[s]);
-        uint32_t* mask_row = nullptr;
-        if (kTrain && tile < ntiles) {
-          mask_row = reinterpret_cast<uint32_t*>(a.cache + cache_mask_offset(a.m) + (size_t)tile * kMaskTileBytes) + row;
-          uint32_t w[16];
-          mask_row[(64 + cg) * kTileM] = neg;
-          pack_group(f, w);
-          stage_store(w, a.cache + (size_t)tile * kCacheTileBytes + cache_slice_off(kCacheH9 + (cg >> 1), q));
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-        if (cg == 0) {
-          float sp = sigma_part[s] + sC[kCB8_0];
+        for (int gi = 0; gi < 2; ++gi) {
+          const int col0 = 64 * blk + 32 * gi;
+          uint32_t v[32];
+          tmem_ld32(t_slot + col0, v);
+          tmem_ld_wait();
+          float f[32];
+          const uint32_t neg = finish_group<true>(v, sC + kCBias9 + col0, f);
 #pragma unroll
-          for (int g = 1; g < 4; ++g) {
-            const float4 o = sX[(s * 128 + row) * 4 + g];
-            rgb0 += o.x, rgb1 += o.y, rgb2 += o.z, sp += o.w;
+          for (int i = 0; i < 32; ++i) {
+            rgb0 = fmaf(f[i], sC[kCWout + col0 + i], rgb0);
+            rgb1 = fmaf(f[i], sC[kCWout + 128 + col0 + i], rgb1);
+            rgb2 = fmaf(f[i], sC[kCWout + 256 + col0 + i], rgb2);
           }
-          if (grow < a.m) {
-            a.sigma[grow] = fmaxf(sp, 0.f);                                  // nerf.py:115
-            a.rgb[3 * grow] = 1.f / (1.f + __expf(-(rgb0 + sC[kCBout])));    // nerf.py:119
-            a.rgb[3 * grow + 1] = 1.f / (1.f + __expf(-(rgb1 + sC[kCBout + 1])));
-            a.rgb[3 * grow + 2] = 1.f / (1.f + __expf(-(rgb2 + sC[kCBout + 2])));
+          if (to_cache) {
+            uint32_t w[16];
+            mask_row[(64 + 2 * blk + gi) * kTileM] = neg;
+            pack_group(f, w);
+            store_words(w, st_row, row, 4 * gi);
           }
-          if (kTrain && tile < ntiles) mask_row[kMaskSigmaWord * kTileM] = (grow < a.m && sp > 0.f) ? 1u : 0u;
         }
-        if (stamp && s == 0) a.prof[((iter * kNumFwdLayers + l) * 8) + 3] = clock64();
+        tc_fence_before();
+        if (blk == 1) sX[slot * 128 + row] = make_float4(rgb0, rgb1, rgb2, sigma_part);
+        if (to_cache) bulk_out(cache_tile + cache_slice_off(kCacheH9 + blk, q));
+        named_bar_sync(1 + slot, 256);  // the slot's eight warps
+        if (blk == 0) {
+          const float4 o = sX[slot * 128 + row];
+          const float sp = sigma_part + o.w + sC[kCB8_0];
+          if (grow < a.m) {
+            a.sigma[grow] = fmaxf(sp, 0.f);                                        // nerf.py:115
+            a.rgb[3 * grow] = 1.f / (1.f + __expf(-(rgb0 + o.x + sC[kCBout])));    // nerf.py:119
+            a.rgb[3 * grow + 1] = 1.f / (1.f + __expf(-(rgb1 + o.y + sC[kCBout + 1])));
+            a.rgb[3 * grow + 2] = 1.f / (1.f + __expf(-(rgb2 + o.z + sC[kCBout + 2])));
+          }
+          if (to_cache) mask_row[kMaskSigmaWord * kTileM] = (grow < a.m && sp > 0.f) ? 1u : 0u;
+        }
+        if (stamp) a.prof[((iter * kNumFwdLayers + l) * 8) + 3] = clock64();
       }
     }
     if (kTrain) {

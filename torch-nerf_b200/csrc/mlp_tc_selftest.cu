@@ -195,11 +195,53 @@ __global__ void __launch_bounds__(640, 1) mma_rate_kernel(int iters, int n, int 
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+// Write-bandwidth probe: every CTA streams 4 KB pieces to a contiguous range, round-robin over the grid.
+//   mode 0: st.global.v4      1: st.global.cs.v4 (streaming)      2: bulk store (TMA engine) from shared memory
+//   mode 3: bulk store with an L2 evict_first cache hint          4: bulk store with an L2 evict_last hint
+__global__ void __launch_bounds__(256) write_bw_kernel(uint8_t* dst, size_t bytes, int mode) {
+  __shared__ __align__(1024) uint8_t buf[4][4096];
+  const size_t pieces = bytes / 4096;
+  for (int i = threadIdx.x; i < 4 * 4096 / 16; i += blockDim.x) reinterpret_cast<uint4*>(&buf[0][0])[i] = make_uint4(i, 1, 2, 3);
+  fence_proxy_async();
+  __syncthreads();
+  if (mode <= 1) {
+    const uint4 v = make_uint4(threadIdx.x, 1, 2, 3);
+    for (size_t p = blockIdx.x; p < pieces; p += gridDim.x) {
+      uint4* d = reinterpret_cast<uint4*>(dst + p * 4096) + threadIdx.x;
+      if (mode == 0) *d = v;
+      else asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(d), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    }
+  } else if (threadIdx.x == 0) {
+    uint64_t policy = 0;
+    if (mode == 3) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    if (mode == 4) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+    int k = 0;
+    for (size_t p = blockIdx.x; p < pieces; p += gridDim.x, ++k) {
+      if (mode == 2)
+        bulk_s2g(dst + p * 4096, buf[k & 3], 4096);
+      else
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst + p * 4096),
+                     "r"(smem_u32(buf[k & 3])), "r"(4096), "l"(policy)
+                     : "memory");
+      bulk_commit();
+      bulk_wait_read<3>();
+    }
+    bulk_wait_all<0>();
+  }
+}
+
 }  // namespace nerf
 
 using namespace nerf;
 
 extern "C" {
+
+int nerf_selftest_write_bw(void* dst_dev, size_t bytes, int mode, int blocks, nerf_stream_t stream) {
+  NERF_CHECK_ARG(dst_dev && bytes >= 4096 && mode >= 0 && mode <= 4 && blocks > 0, "nerf_selftest_write_bw: bad arguments");
+  write_bw_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<uint8_t*>(dst_dev), bytes, mode);
+  NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
 
 int nerf_selftest_umma(const uint16_t* a_dev, const uint16_t* b_dev, float* d_dev, int n, int k, int variant,
                        nerf_stream_t stream) {
