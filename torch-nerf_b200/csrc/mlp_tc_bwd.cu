@@ -482,6 +482,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
   __shared__ Segment segs[kNumWUnits];
   __shared__ int nseg_s;
+  __shared__ uint32_t stage_base[kWgMaxStages];  // completed phases of every stage's barriers (segments change the ring geometry)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ntiles = num_tiles(a.m);
@@ -492,6 +493,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
     }
     mbar_init(acc_done, 1);
     fence_barrier_init();
+    for (int i = 0; i < kWgMaxStages; ++i) stage_base[i] = 0;
     nseg_s = build_segments(ntiles, segs);
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -517,11 +519,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
     const uint32_t bytes = head_off + (u.head ? 512u : 0u);
     const uint32_t stage_bytes = (bytes + 1023u) & ~1023u;
     const uint32_t nst = min((uint32_t)kWgMaxStages, (uint32_t)kWgRingBytes / stage_bytes);
+    uint32_t phase_bits0 = 0;  // parity of the next phase of every stage's barriers at the start of this segment
+#pragma unroll
+    for (int i = 0; i < kWgMaxStages; ++i) phase_bits0 |= (stage_base[i] & 1u) << i;
 
     if (warp == 0) {
       // ---------------------------------------------------------------- loader: 32-row slices of every block
       const bool leader = elect_one();
-      uint32_t g = 0;
+      uint32_t g = 0, s = 0, phase_bits = phase_bits0;  // stage cursor; bit i = parity of stage i's next phase
       long long ld_wait = 0;
       const long long ld_t0 = a.prof ? clock64() : 0;
       const uint8_t* ghead = a.scratch + scratch_ghead_offset(a.m);
@@ -529,7 +534,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
         const uint8_t* gtile = a.scratch + (size_t)tile * kGradTileBytes;
         const uint8_t* xtile = a.cache + (size_t)tile * kCacheTileBytes;
         for (int sl = 0; sl < 4; ++sl) {
-          const uint32_t s = g % nst, ph = (g / nst) & 1;
+          const uint32_t ph = (phase_bits >> s) & 1u;
           const long long w0 = a.prof ? clock64() : 0;
           mbar_wait(&empty[s], ph ^ 1);
           if (a.prof) ld_wait += clock64() - w0;
@@ -543,6 +548,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
             if (u.head) bulk_g2s(dst + head_off, ghead + ((size_t)tile * kTileM + sl * 32) * 16, 512, &full[s]);
           }
           __syncwarp();
+          phase_bits ^= 1u << s;
+          s = (s + 1 == nst) ? 0u : s + 1;
           ++g;
         }
       }
@@ -553,7 +560,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
     } else if (warp == 1) {
       // ---------------------------------------------------------------- MMA issuer (MN-major operands)
       const bool leader = elect_one();
-      uint32_t g = 0;
+      uint32_t g = 0, s = 0, phase_bits = phase_bits0;  // stage cursor; bit i = parity of stage i's next phase
       const uint32_t sm_u = smem_u32(smem);
       const int nhalf = u.n_gblk / 2;
       const uint32_t n_main = (uint32_t)u.n_xblk * 64u;
@@ -564,7 +571,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
       const long long mma_t0 = a.prof ? clock64() : 0;
       for (int64_t tile = tile0; tile < tile1; ++tile) {
         for (int sl = 0; sl < 4; ++sl) {
-          const uint32_t s = g % nst, ph = (g / nst) & 1;
+          const uint32_t ph = (phase_bits >> s) & 1u;
           const long long w0 = a.prof ? clock64() : 0;
           mbar_wait(&full[s], ph);
           if (a.prof) mma_wait += clock64() - w0;
@@ -588,6 +595,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
           }
           first = false;
           __syncwarp();
+          phase_bits ^= 1u << s;
+          s = (s + 1 == nst) ? 0u : s + 1;
           ++g;
         }
       }
@@ -609,12 +618,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
       float hb = 0.f;  // head bias sums (threads 0..127: one row and component each)
       const int b_cg = b_ncg ? t % b_ncg : 0, b_rows = b_ncg / 8, b_r0 = b_ncg ? (t / b_ncg) * b_rows : 0;
       const int h_cg = h_ncg ? t % h_ncg : 0, h_rows = h_ncg / 8, h_r0 = h_ncg ? (t / h_ncg) * h_rows : 0;
-      uint32_t g = 0;
+      uint32_t g = 0, s = 0, phase_bits = phase_bits0;  // stage cursor; bit i = parity of stage i's next phase
       long long cc_wait = 0;
       const long long cc_t0 = a.prof ? clock64() : 0;
       for (int64_t tile = tile0; tile < tile1; ++tile) {
         for (int sl = 0; sl < 4; ++sl) {
-          const uint32_t s = g % nst, ph = (g / nst) & 1;
+          const uint32_t ph = (phase_bits >> s) & 1u;
           const long long w0 = a.prof ? clock64() : 0;
           mbar_wait(&full[s], ph);
           if (a.prof) cc_wait += clock64() - w0;
@@ -630,6 +639,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&empty[s]);
+          phase_bits ^= 1u << s;
+          s = (s + 1 == nst) ? 0u : s + 1;
           ++g;
         }
       }
@@ -694,17 +705,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
       }
       tc_fence_before();
     }
-    // ---- segment boundary: the next unit uses another ring geometry, so the ring is drained and its barriers start over
+    // ---- segment boundary: the next unit uses another ring geometry.  The ring is drained here (every stage consumed
+    //      and released); the barriers keep their state, only the number of phases each one has completed is recorded
     __syncthreads();
     if (si + 1 < nseg) {
       if (threadIdx.x == 0) {
-        for (int i = 0; i < kWgMaxStages; ++i) {
-          mbar_inval(&full[i]);
-          mbar_inval(&empty[i]);
-          mbar_init(&full[i], 1);
-          mbar_init(&empty[i], 1 + kWgCudaWarps);
-        }
-        fence_barrier_init();
+        const uint32_t total = (uint32_t)(tile1 - tile0) * 4u;  // stages streamed in this segment
+        for (uint32_t i = 0; i < nst; ++i)
+          if (total > i) stage_base[i] += (total - i + nst - 1) / nst;
       }
       __syncthreads();
       tc_fence_after();
