@@ -16,7 +16,7 @@ cache = torch.empty(lib.nerf_mlp_bf16_cache_bytes(m), dtype=torch.uint8, device=
 def fwd(c):
     tn._lib.check(lib.nerf_mlp_bf16_forward(P(packed, torch.uint8), None, None, P(ray_o), P(ray_d), P(t), s, m, P(sig), P(rgb),
                                             P(c, torch.uint8) if c is not None else None, tn._lib.stream()), "fwd")
-for mode, label in ((0, "normal"), (1, "no block stores"), (2, "stores wrapped onto 64 tiles"), (0, "normal again")):
+for mode, label in ((0, "normal"), (1, "no block stores"), (2, "stores wrapped onto 64 tiles"), (3, "no STS, no block stores"), (0, "normal again")):
     lib.nerf_debug_set_profile_buffer(None, mode << 16)
     fwd(cache); torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

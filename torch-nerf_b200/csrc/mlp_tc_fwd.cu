@@ -370,6 +370,31 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
       __syncwarp();
     };
 
+    // this thread's input row of a tile: the sample position (block 0 warps) or the view direction (block 1 warps)
+    const bool is_pe = blk == 0;
+    auto load_xyz = [&](int64_t tile_, float& x, float& y, float& z) {
+      const int64_t grow_ = tile_ * kTileM + row;
+      x = y = z = 0.f;
+      if (grow_ < a.m) {
+        if (a.pts != nullptr) {
+          const float* src = is_pe ? a.pts : a.dirs;
+          x = __ldg(src + 3 * grow_), y = __ldg(src + 3 * grow_ + 1), z = __ldg(src + 3 * grow_ + 2);
+        } else {
+          const int64_t ray = a.m < (int64_t(1) << 31) ? (int64_t)((uint32_t)grow_ / (uint32_t)a.s) : grow_ / a.s;
+          x = __ldg(a.ray_d + 3 * ray), y = __ldg(a.ray_d + 3 * ray + 1), z = __ldg(a.ray_d + 3 * ray + 2);
+          if (is_pe) {
+            const float tt = __ldg(a.t + grow_);
+            // stratified_sampler.py:126: o + t*d, product and sum rounded separately
+            x = __fadd_rn(__ldg(a.ray_o + 3 * ray), __fmul_rn(tt, x));
+            y = __fadd_rn(__ldg(a.ray_o + 3 * ray + 1), __fmul_rn(tt, y));
+            z = __fadd_rn(__ldg(a.ray_o + 3 * ray + 2), __fmul_rn(tt, z));
+          }
+        }
+      }
+    };
+    float x, y, z;
+    load_xyz(2 * (int64_t)blockIdx.x + slot, x, y, z);
+
     for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++iter) {
       const bool stamp = a.prof != nullptr && blockIdx.x == 0 && iter < a.prof_tiles && warp == 2 && lane == 0;
       const int64_t tile = 2 * pair + slot;
@@ -380,24 +405,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
           kTrain ? reinterpret_cast<uint32_t*>(a.cache + cache_mask_offset(a.m) + (size_t)tile * kMaskTileBytes) + row : nullptr;
       // ---- encoded inputs (cube.py:62-69): block 0 warps encode the point, block 1 warps the view direction
       {
-        const bool is_pe = blk == 0;
-        float x = 0.f, y = 0.f, z = 0.f;
-        if (grow < a.m) {
-          if (a.pts != nullptr) {
-            const float* src = is_pe ? a.pts : a.dirs;
-            x = __ldg(src + 3 * grow), y = __ldg(src + 3 * grow + 1), z = __ldg(src + 3 * grow + 2);
-          } else {
-            const int64_t ray = grow / a.s;
-            x = __ldg(a.ray_d + 3 * ray), y = __ldg(a.ray_d + 3 * ray + 1), z = __ldg(a.ray_d + 3 * ray + 2);
-            if (is_pe) {
-              const float tt = __ldg(a.t + grow);
-              // stratified_sampler.py:126: o + t*d, product and sum rounded separately
-              x = __fadd_rn(__ldg(a.ray_o + 3 * ray), __fmul_rn(tt, x));
-              y = __fadd_rn(__ldg(a.ray_o + 3 * ray + 1), __fmul_rn(tt, y));
-              z = __fadd_rn(__ldg(a.ray_o + 3 * ray + 2), __fmul_rn(tt, z));
-            }
-          }
-        }
         if (is_pe) {
           if (kTrain) staging_free();  // also covers the previous pair's store out of the pe block (same thread's groups)
           encode_row<10, 8, false>(x, y, z, sIn + slot * kBlockBytes + row * 128, 0, nullptr, row);
@@ -497,6 +504,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
           if (stamp) a.prof[((iter * kNumFwdLayers + l) * 8) + 3] = clock64();
         }
       }
+      // the next tile's coordinates: in flight while fc_9 is still in the tensor pipe
+      load_xyz(2 * (pair + gridDim.x) + slot, x, y, z);
       // ---- fc_9 output (128 columns = one N-half): this warp owns columns [64 blk, 64 blk + 64)
       {
         const int l = kNumFwdLayers - 1;
