@@ -199,8 +199,14 @@ int nerf_debug_set_bwd_phases(int mask);
  * 5/6 tiles of the first / second segment.  Pass NULL to switch it off. */
 int nerf_debug_set_wgrad_profile(unsigned long long* buf_dev);
 
+/* self test + rate probe of the CTA-pair MMA (tcgen05 cta_group::2, M = 256): a (256 x k), b (n x k) bf16 bits, d (256 x n)
+ * fp32, all row-major; ts != 0 puts the A operand in tensor memory.  `pairs` clusters of two CTAs all compute the same
+ * product; with iters > 0 each leader then times iters x (k/16) MMAs into cycles_dev[pair]. */
+int nerf_selftest_umma2(const uint16_t* a_dev, const uint16_t* b_dev, float* d_dev, int n, int k, int ts, int pairs, int iters,
+                        unsigned long long* cycles_dev, nerf_stream_t stream);
+
 /* micro-benchmark: `blocks` CTAs each issue `iters` x 4 tcgen05.mma (M=128, N=n, K=16) -- mode bit 0: A operand from TMEM instead of
- * shared memory; bit 1: tcgen05.commit after every group of 4; bit 2: probe a completed mbarrier before every group -- while `bg_warps` extra warps each perform `bg_iters` tcgen05.ld
+ * shared memory; bit 1: tcgen05.commit after every group of 4; bit 2: probe a completed mbarrier before every group; bit 4: alternate between two accumulators -- while `bg_warps` extra warps each perform `bg_iters` tcgen05.ld
  * (bg_store = 0) or tcgen05.st (1) of 32 lanes x 32 columns.  cycles_dev[block] = SM cycles of the MMA thread,
  * cycles_dev[blocks + block] = cycles of one background warp.  cycles_dev holds 2*blocks entries. */
 int nerf_selftest_mma_rate(int blocks, int iters, int n, int mode, int bg_warps, int bg_iters, int bg_store,

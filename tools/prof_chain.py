@@ -22,6 +22,12 @@ if "--micro" in sys.argv:
         for flags, label in ((2, "commit per 4"), (4, "probe per 4"), (6, "commit+probe per 4"), (8, "syncwarp per 4"), (14, "all three")):
             m, _ = rate(148, 2000, n, 1 | flags)
             print(f"mma TS N={n:3d} + {label:20s}: {m:6.1f} cycles/MMA")
+    for mode, n in ((16, 128), (17, 128), (17, 64)):
+        m, _ = rate(148, 2000, n, mode)
+        print(f"mma alternating two accumulators mode={'SS' if (mode & 1) == 0 else 'TS'} N={n:3d}: {m:6.1f} cycles/MMA (floor {128 * n / 256:.0f})")
+    for mode, n in ((33, 128), (33, 64), (32, 128)):
+        m, _ = rate(148, 2000, n, mode)
+        print(f"two issuer warps, own accumulators, mode={'SS' if (mode & 1) == 0 else 'TS'} N={n:3d}: {m / 2:6.1f} cycles/MMA aggregate ({m:6.1f} per issuer)")
     if "--short" in sys.argv:
         sys.exit(0)
     for w in (1, 4, 8, 16):

@@ -67,6 +67,7 @@ _PROTOTYPES = {
     "nerf_debug_set_bwd_phases": (c_int, [c_int]),
     "nerf_debug_set_wgrad_profile": (c_int, [_P]),
     "nerf_selftest_mma_rate": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "nerf_selftest_umma2": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "nerf_selftest_write_bw": (c_int, [_P, c_size_t, c_int, c_int, _P]),
 }
 

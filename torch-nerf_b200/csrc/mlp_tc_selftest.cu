@@ -114,6 +114,106 @@ __global__ void __launch_bounds__(128, 1) selftest_umma_kernel(const uint16_t* _
 
 
 // ------------------------------------------------------------------------------------------------
+// self test + rate probe of the CTA-pair MMA (cta_group::2, M = 256): a (256 x k), b (n x k), d (256 x n) row-major.
+// CTA r of the pair holds rows [128 r, +128) of A (shared memory, or tensor memory when ts != 0) and of D, and rows
+// [n/2 r, +n/2) of B.  With iters > 0 the leader afterwards times iters x (k/16) MMAs: cycles[pair] = SM cycles.
+// ------------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+    selftest_umma2_kernel(const uint16_t* __restrict__ a, const uint16_t* __restrict__ b, float* __restrict__ d, int n, int k,
+                          int ts, int iters, unsigned long long* __restrict__ cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar[2];
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int nkb = k / 64, nh = n / 2;
+  const uint32_t a_blk = 128 * 128, b_blk = (uint32_t)nh * 128;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + nkb * a_blk;
+  for (int e = threadIdx.x; e < 128 * k; e += 128) {
+    int r = e / k, c = e % k;
+    *reinterpret_cast<uint16_t*>(sA + (c / 64) * a_blk + tile_off(r, c % 64)) = a[(size_t)(rank * 128 + r) * k + c];
+  }
+  for (int e = threadIdx.x; e < nh * k; e += 128) {
+    int r = e / k, c = e % k;
+    *reinterpret_cast<uint16_t*>(sB + (c / 64) * b_blk + tile_off(r, c % 64)) = b[(size_t)(rank * nh + r) * k + c];
+  }
+  fence_proxy_async();
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc2(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (ts) {
+    const int row = warp * 32 + lane;
+    for (int kb = 0; kb < nkb; ++kb) {
+      uint32_t w[32];
+      for (int c = 0; c < 32; ++c) {
+        const size_t off = (size_t)(rank * 128 + row) * k + kb * 64 + 2 * c;
+        w[c] = (uint32_t)a[off] | ((uint32_t)a[off + 1] << 16);
+      }
+      tmem_st32(tmem_base + ((uint32_t)(warp * 32) << 16) + 256 + kb * 32, w);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+  }
+  const uint32_t idesc = make_idesc_bf16_m256((uint32_t)n);
+  auto issue_all = [&]() {
+    for (int kk = 0; kk < k / 16; ++kk) {
+      const uint64_t db = desc_kmajor(smem_u32(sB) + (kk / 4) * b_blk + (kk % 4) * 32);
+      if (ts) {
+        umma2_bf16_ts(tmem_base, tmem_base + 256 + 8 * kk, db, idesc, kk > 0 ? 1u : 0u);
+      } else {
+        const uint64_t da = desc_kmajor(smem_u32(sA) + (kk / 4) * a_blk + (kk % 4) * 32);
+        umma2_bf16(tmem_base, da, db, idesc, kk > 0 ? 1u : 0u);
+      }
+    }
+  };
+  if (rank == 0 && threadIdx.x == 0) {
+    issue_all();
+    umma2_commit(&bar[0], 3);
+  }
+  mbar_wait(&bar[0], 0);
+  tc_fence_after();
+  const int row = warp * 32 + lane;
+  for (int c = 0; c < n / 32; ++c) {
+    uint32_t v[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c * 32, v);
+    tmem_ld_wait();
+    for (int i = 0; i < 32; ++i) d[(size_t)(rank * 128 + row) * n + c * 32 + i] = __uint_as_float(v[i]);
+  }
+  if (iters > 0) {
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    if (rank == 0 && threadIdx.x == 0) {
+      const long long t0 = clock64();
+      for (int it = 0; it < iters; ++it) issue_all();
+      umma2_commit(&bar[1], 3);
+      mbar_wait(&bar[1], 0);
+      cycles[blockIdx.x / 2] = (unsigned long long)(clock64() - t0);
+    } else {
+      mbar_wait(&bar[1], 0);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc2(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
 // micro-benchmark: sustained tcgen05.mma issue rate of one CTA per SM (M=128, K=16 per instruction)
 //   mode 0: A and B from shared memory (SS), N = n;   mode 1: A from TMEM (TS), B from shared memory
 // out[block] = cycles for `iters` groups of 4 MMAs (one 64-wide k-block), measured by the issuing thread.
@@ -143,12 +243,15 @@ __global__ void __launch_bounds__(640, 1) mma_rate_kernel(int iters, int n, int 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  if (warp == 0 && iters > 0) {
-    // issue pattern of the chain kernels: the whole warp runs the loop, one elected lane issues
+  if ((warp == 0 || (warp == 1 && (mode & 32))) && iters > 0) {
+    // issue pattern of the chain kernels: the whole warp runs the loop, one elected lane issues.  mode bit 5: warp 1
+    // is a second issuer working on its own accumulator (columns [128,256)) and its own completion barrier
     const bool leader = elect_one();
     const uint32_t idesc = make_idesc_bf16((uint32_t)n, false, false);
     const uint64_t da = desc_kmajor(smem_u32(smem));
     const uint64_t db = desc_kmajor(smem_u32(smem) + 16384);
+    uint64_t* done = warp == 0 ? &bar : &bar2[0];
+    const uint32_t acc0 = tmem_base + (warp == 1 ? 128u : 0u);
     const long long t0 = clock64();
     const int m = mode & 1;
     for (int it = 0; it < iters; ++it) {
@@ -156,18 +259,20 @@ __global__ void __launch_bounds__(640, 1) mma_rate_kernel(int iters, int n, int 
       if (leader) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          if (m == 0) umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, 1u);
-          else umma_bf16_ts(tmem_base, tmem_base + 256 + 8 * k, db + 2 * k, idesc, 1u);
+          // mode bit 4: successive MMAs alternate between two independent accumulators (columns 0 and 128; n <= 128)
+          const uint32_t acc = acc0 + (((mode & 16) && (k & 1)) ? 128u : 0u);
+          if (m == 0) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, 1u);
+          else umma_bf16_ts(acc, tmem_base + 256 + 8 * k, db + 2 * k, idesc, 1u);
         }
-        if (mode & 2) umma_commit(&bar2[0]);  // commit after every group (nobody waits on it)
+        if ((mode & 2) && warp == 0) umma_commit(&bar2[0]);  // commit after every group (nobody waits on it)
       }
       if (mode & 8) __syncwarp();
     }
-    if (leader) umma_commit(&bar);
+    if (leader) umma_commit(done);
     __syncwarp();
-    mbar_wait(&bar, 0);
+    mbar_wait(done, 0);
     const long long t1 = clock64();
-    if (lane == 0) out[blockIdx.x] = (unsigned long long)(t1 - t0);
+    if (lane == 0 && warp == 0) out[blockIdx.x] = (unsigned long long)(t1 - t0);
   }
   if (warp >= 4 && warp < 4 + bg_warps) {
     // background tensor-memory traffic on columns [384,512) (not touched by the MMAs)
@@ -255,9 +360,22 @@ int nerf_selftest_umma(const uint16_t* a_dev, const uint16_t* b_dev, float* d_de
   return NERF_OK;
 }
 
+int nerf_selftest_umma2(const uint16_t* a_dev, const uint16_t* b_dev, float* d_dev, int n, int k, int ts, int pairs, int iters,
+                        unsigned long long* cycles_dev, nerf_stream_t stream) {
+  NERF_CHECK_ARG(a_dev && b_dev && d_dev, "nerf_selftest_umma2: null pointer");
+  NERF_CHECK_ARG(n >= 32 && n <= 256 && n % 32 == 0 && k >= 64 && k <= 256 && k % 64 == 0 && pairs >= 1 && iters >= 0 &&
+                     (iters == 0 || cycles_dev),
+                 "nerf_selftest_umma2: n multiple of 32 in [32,256], k multiple of 64 in [64,256]");
+  size_t smem = (size_t)128 * k * 2 + (size_t)(n / 2) * k * 2 + 1024;
+  NERF_CUDA(cudaFuncSetAttribute(selftest_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  selftest_umma2_kernel<<<2 * pairs, 128, smem, as_stream(stream)>>>(a_dev, b_dev, d_dev, n, k, ts, iters, cycles_dev);
+  NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
+
 int nerf_selftest_mma_rate(int blocks, int iters, int n, int mode, int bg_warps, int bg_iters, int bg_store,
                            unsigned long long* cycles_dev, nerf_stream_t stream) {
-  NERF_CHECK_ARG(cycles_dev && blocks > 0 && iters >= 0 && n >= 16 && n <= 256 && n % 16 == 0 && mode >= 0 && mode < 16 &&
+  NERF_CHECK_ARG(cycles_dev && blocks > 0 && iters >= 0 && n >= 16 && n <= 256 && n % 16 == 0 && mode >= 0 && mode < 64 &&
                      bg_warps >= 0 && bg_warps <= 16 && bg_iters >= 0,
                  "nerf_selftest_mma_rate: bad arguments");
   const size_t smem = 16384 + 32768 + 1024;
