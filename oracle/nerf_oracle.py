@@ -503,3 +503,34 @@ def pose_spherical(theta_deg: float, phi_deg: float, radius: float) -> np.ndarra
 def blender_focal(img_w: int, camera_angle_x: float = 0.6911112070083618) -> float:
     """utils/data/load_blender.py:170-171 -- focal = 0.5 W / tan(0.5 camera_angle_x)."""
     return float(0.5 * img_w / np.tan(0.5 * camera_angle_x))
+
+
+# ------------------------------------------------------------------------------------------------
+# callers of the path (section 8f): the pieces of the training loop that are arithmetic
+# ------------------------------------------------------------------------------------------------
+def center_crop_pixel_indices(img_h: int, img_w: int) -> np.ndarray:
+    """runners/train.py:151-167 -- flat pixel ids (row * W + col) of the central block sampled while epoch < 10:
+    the cartesian product of arange(ci - ci//2, ci + ci//2) x arange(cj - cj//2, cj + cj//2), rows outermost."""
+    ci, cj = (img_h - 1) // 2, (img_w - 1) // 2
+    out = []
+    for i in range(ci - ci // 2, ci + ci // 2):
+        for j in range(cj - cj // 2, cj + cj // 2):
+            out.append(i * img_w + j)
+    return np.asarray(out, dtype=np.int64)
+
+
+def exp_lr_gamma(init_lr: float, end_lr: float, num_iter: int) -> float:
+    """runners/runner_utils.py:704-708 -- per-iteration decay of ExponentialLR."""
+    return pow(end_lr / init_lr, 1 / num_iter)
+
+
+def adam_step(p, g, m, v, step: int, lr: float, eps: float = 1e-8, b1: float = 0.9, b2: float = 0.999):
+    """torch.optim.Adam (runner_utils.py:691-695: lr, eps given; betas, weight_decay = defaults), single tensor,
+    fp32 state like torch: returns the new (p, m, v) after update number `step` (1-based)."""
+    F = np.float32
+    m = (F(b1) * m + F(1 - b1) * g).astype(F)
+    v = (F(b2) * v + F(1 - b2) * g * g).astype(F)
+    bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
+    denom = (np.sqrt(v) / F(np.sqrt(bc2)) + F(eps)).astype(F)
+    p = (p - F(lr / bc1) * (m / denom)).astype(F)
+    return p, m, v

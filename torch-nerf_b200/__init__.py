@@ -10,9 +10,11 @@ from .ray_samplers import RayBundle, RaySamplerBase, StratifiedSampler, make_bin
 from .scene import PrimitiveBase, PrimitiveCube
 from .signal_encoder import PositionalEncoder, SignalEncoderBase
 from .volume_renderer import VolumeRenderer
+from . import checkpoint
+from .trainer import Trainer, center_crop_pixel_indices, exp_lr_gamma
 
 __all__ = [
     "PerspectiveCamera", "IntegratorBase", "QuadratureIntegrator", "NeRF", "RayBundle", "RaySamplerBase",
     "StratifiedSampler", "make_bins", "sample_pdf", "PrimitiveBase", "PrimitiveCube", "PositionalEncoder",
-    "SignalEncoderBase", "VolumeRenderer",
+    "SignalEncoderBase", "VolumeRenderer", "Trainer", "checkpoint", "center_crop_pixel_indices", "exp_lr_gamma",
 ]
