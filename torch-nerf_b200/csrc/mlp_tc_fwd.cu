@@ -43,7 +43,7 @@ using namespace tc;
 constexpr int kMaxStages = 10;
 template <bool kTrain>
 struct FwdCfg {
-  static constexpr int kStages = kTrain ? 6 : 10;  // inference uses the staging area as four more weight stages
+  static constexpr int kStages = 6;  // (ring depth 6 .. 10 measured equal)
 };
 constexpr int kEpiWarps = 16;
 constexpr int kSlotThreads = kEpiWarps * 32 / 2;   // epilogue threads serving one tile slot
@@ -54,12 +54,11 @@ constexpr int kSmIn = 0;                        // pe block slot X | pe block sl
 constexpr int kSmC = 3 * kBlockBytes;           // fp32 constants
 constexpr int kSmX = kSmC + kCFloats * 4;       // 2 slots x 128 rows x {rgb0, rgb1, rgb2, sigma} partial sums of block 1
 constexpr int kSmBar = kSmX + 2 * 128 * 16;
-constexpr int kSmStage = (kSmBar + 512 + 1023) / 1024 * 1024;  // training: 16 warps x 4 KB staging slices
-constexpr int kSmWTrain = kSmStage + 65536;     // weight ring (training)
-constexpr int kSmWInfer = kSmStage;             // weight ring (inference)
-constexpr int kSmTotal = kSmStage + kMaxStages * kChunkBytes;
+constexpr int kSmStage = (kSmBar + 512 + 1023) / 1024 * 1024;  // training: 16 warps x 4 KB staging slices;
+                                                               // inference: second set of the three input blocks
+constexpr int kSmW = kSmStage + 65536;          // weight ring
+constexpr int kSmTotal = kSmW + 6 * kChunkBytes;
 constexpr int kFwdSmemBytes = kSmTotal + 1024;  // + alignment slack
-static_assert(kSmWTrain + 6 * kChunkBytes <= kSmTotal, "training ring fits");
 static_assert(kFwdSmemBytes <= 232448, "shared memory budget");
 // tensor memory map (columns), per slot
 constexpr uint32_t kTmSlot = 256;
@@ -201,7 +200,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sIn = smem + kSmIn;
   uint8_t* sStage = smem + kSmStage;
-  uint8_t* sW = smem + (kTrain ? kSmWTrain : kSmWInfer);
+  uint8_t* sW = smem + kSmW;
   float* sC = reinterpret_cast<float*>(smem + kSmC);
   float4* sX = reinterpret_cast<float4*>(smem + kSmX);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmBar);
@@ -211,7 +210,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
   uint64_t* a_ready = in_ready + 2;           // [2] per slot: layer input rewritten in TMEM (one completion per layer 0..8)
   uint64_t* acc_free = a_ready + 2;           // [2] per slot: N-half 0 pulled out of the accumulator
   uint64_t* acc_full = acc_free + 2;          // [2] per slot: the MMAs of one N-half have completed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
+  uint64_t* drained = acc_full + 2;           // [2] per slot (inference): fc_9's accumulator has been read
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(drained + 2);
+  // Inference double-buffers the encoded inputs (second set in the unused staging area): the next tile's inputs are
+  // written during the current tile's last layers, so the first MMAs of a tile only wait for the accumulator.
+  constexpr bool kEarlyInputs = !kTrain;
+  uint8_t* const in_set[2] = {sIn, kEarlyInputs ? sStage : sIn};
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ntiles = num_tiles(a.m);
@@ -231,6 +235,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
       mbar_init(&a_ready[i], kSlotThreads);
       mbar_init(&acc_free[i], kSlotThreads);
       mbar_init(&acc_full[i], 1);
+      mbar_init(&drained[i], kSlotThreads);
     }
     fence_barrier_init();
   }
@@ -268,14 +273,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
     uint32_t g = 0, n_in = 0, n_a = 0, n_free = 0;
     constexpr uint32_t idesc = make_idesc_bf16(128, false, false);
     const uint32_t sW_u = smem_u32(sW);
-    const uint32_t sPe_u = smem_u32(sIn) + (uint32_t)slot * kBlockBytes;
-    const uint32_t sDe_u = smem_u32(sIn) + 2u * kBlockBytes + (uint32_t)slot * 64u;
     const uint32_t acc = tmem_base + (uint32_t)slot * kTmSlot;
     const uint32_t a_tm = acc + kTmA;
     int iter = 0;
     for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++iter) {
       mbar_wait(&in_ready[slot], n_in & 1);
       ++n_in;
+      if (kEarlyInputs && iter > 0) mbar_wait(&drained[slot], (uint32_t)(iter - 1) & 1);  // previous tile's fc_9 is out
+      const uint32_t sPe_u = smem_u32(in_set[iter & 1]) + (uint32_t)slot * kBlockBytes;
+      const uint32_t sDe_u = smem_u32(in_set[iter & 1]) + 2u * kBlockBytes + (uint32_t)slot * 64u;
       for (int l = 0; l < kNumFwdLayers; ++l) {
         const int nk = fwd_nk(l);
         const bool stamp = a.prof != nullptr && blockIdx.x == 0 && iter < a.prof_tiles && slot == 0;
@@ -392,7 +398,32 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
         }
       }
     };
-    float x, y, z;
+    float x, y, z;  // this thread's input row of the tile that is encoded next
+    // ---- encoded inputs (cube.py:62-69) of tile `tile_` into one input set: block 0 warps encode the point, block 1
+    //      warps the view direction; then in_ready.  (Training: the pe block also goes to the cache by bulk store.)
+    auto encode_inputs = [&](uint8_t* set, int64_t tile_, uint8_t* cache_tile_, bool to_cache_) {
+      if (is_pe) {
+        if (kTrain) staging_free();  // also covers the previous pair's store out of the pe block (same thread's groups)
+        encode_row<10, 8, false>(x, y, z, set + slot * kBlockBytes + row * 128, 0, nullptr, row);
+        fence_proxy_async();
+        if (kTrain) {
+          __syncwarp();
+          if (lane == 0 && to_cache_) {
+            bulk_s2g(cache_tile_ + cache_slice_off(kCachePe, q), set + slot * kBlockBytes + q * 4096, 4096);
+            bulk_commit();
+          }
+        }
+      } else {
+        if (kTrain && to_cache_)
+          encode_row<4, 4, true>(x, y, z, set + 2 * kBlockBytes + row * 128, 4 * slot,
+                                 cache_tile_ + cache_slice_off(kCacheDe, q) + lane * 128, row);
+        else
+          encode_row<4, 4, false>(x, y, z, set + 2 * kBlockBytes + row * 128, 4 * slot, nullptr, row);
+        fence_proxy_async();
+      }
+      (void)tile_;
+      mbar_arrive(&in_ready[slot]);  // training: inputs written AND this thread has left the slot's previous tile
+    };
     load_xyz(2 * (int64_t)blockIdx.x + slot, x, y, z);
 
     for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++iter) {
@@ -403,29 +434,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
       uint8_t* cache_tile = kTrain ? a.cache + (size_t)tile * kCacheTileBytes : nullptr;
       uint32_t* mask_row =
           kTrain ? reinterpret_cast<uint32_t*>(a.cache + cache_mask_offset(a.m) + (size_t)tile * kMaskTileBytes) + row : nullptr;
-      // ---- encoded inputs (cube.py:62-69): block 0 warps encode the point, block 1 warps the view direction
-      {
-        if (is_pe) {
-          if (kTrain) staging_free();  // also covers the previous pair's store out of the pe block (same thread's groups)
-          encode_row<10, 8, false>(x, y, z, sIn + slot * kBlockBytes + row * 128, 0, nullptr, row);
-          fence_proxy_async();
-          if (kTrain) {
-            __syncwarp();
-            if (lane == 0 && to_cache) {
-              bulk_s2g(cache_tile + cache_slice_off(kCachePe, q), sIn + slot * kBlockBytes + q * 4096, 4096);
-              bulk_commit();
-            }
-          }
-        } else {
-          if (to_cache)
-            encode_row<4, 4, true>(x, y, z, sIn + 2 * kBlockBytes + row * 128, 4 * slot,
-                                   cache_tile + cache_slice_off(kCacheDe, q) + lane * 128, row);
-          else
-            encode_row<4, 4, false>(x, y, z, sIn + 2 * kBlockBytes + row * 128, 4 * slot, nullptr, row);
-          fence_proxy_async();
-        }
-        mbar_arrive(&in_ready[slot]);  // inputs written AND this thread has left the slot's previous tile
-      }
+      if (!kEarlyInputs || iter == 0) encode_inputs(in_set[0], tile, cache_tile, to_cache);
+      if (kEarlyInputs) load_xyz(2 * (pair + gridDim.x) + slot, x, y, z);  // consumed during layer 8 of this tile
       float sigma_part = 0.f;
       uint32_t wh[2][16];  // bf16 pairs of N-half 0, held until half 1's MMAs have stopped reading the layer input
 #pragma unroll 1
@@ -504,8 +514,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
           if (stamp) a.prof[((iter * kNumFwdLayers + l) * 8) + 3] = clock64();
         }
       }
-      // the next tile's coordinates: in flight while fc_9 is still in the tensor pipe
-      load_xyz(2 * (pair + gridDim.x) + slot, x, y, z);
+      if (kEarlyInputs) {
+        // the next tile's encoded inputs go into the other input set while fc_9 is still in the tensor pipe
+        encode_inputs(in_set[(iter + 1) & 1], 0, nullptr, false);
+      } else {
+        // the next tile's coordinates: in flight while fc_9 is still in the tensor pipe
+        load_xyz(2 * (pair + gridDim.x) + slot, x, y, z);
+      }
       // ---- fc_9 output (128 columns = one N-half): this warp owns columns [64 blk, 64 blk + 64)
       {
         const int l = kNumFwdLayers - 1;
@@ -515,12 +530,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
         if (stamp) a.prof[((iter * kNumFwdLayers + l) * 8) + 2] = clock64();
         if (kTrain) staging_free();
         float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
-#pragma unroll
-        for (int gi = 0; gi < 2; ++gi) {
+        uint32_t v0[32], v1[32];
+        tmem_ld32(t_slot + 64 * blk, v0);
+        tmem_ld32(t_slot + 64 * blk + 32, v1);
+        tmem_ld_wait();
+        tc_fence_before();
+        if (kEarlyInputs) mbar_arrive(&drained[slot]);  // the next tile's first MMAs may overwrite the accumulator
+        auto head_group = [&](const uint32_t (&v)[32], int gi) {
           const int col0 = 64 * blk + 32 * gi;
-          uint32_t v[32];
-          tmem_ld32(t_slot + col0, v);
-          tmem_ld_wait();
           float f[32];
           const uint32_t neg = finish_group<true>(v, sC + kCBias9 + col0, f);
 #pragma unroll
@@ -535,8 +552,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
             pack_group(f, w);
             store_words(w, st_row, row, 4 * gi);
           }
-        }
-        tc_fence_before();
+        };
+        head_group(v0, 0);
+        head_group(v1, 1);
         if (blk == 1) sX[slot * 128 + row] = make_float4(rgb0, rgb1, rgb2, sigma_part);
         if (to_cache) bulk_out(cache_tile + cache_slice_off(kCacheH9 + blk, q));
         named_bar_sync(1 + slot, 256);  // the slot's eight warps
