@@ -138,3 +138,19 @@ def test_umma_a_from_tmem(tn, n, k):
     d = _umma(tn, a.view(torch.int16), b.view(torch.int16), n, k, 2)
     ref = a.float() @ b.float().t()
     torch.testing.assert_close(d, ref, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("n,k,ts", [(128, 256, 0), (128, 256, 1), (256, 64, 1), (64, 128, 0)])
+def test_umma_cta_pair(tn, n, k, ts):
+    """cta_group::2: two CTAs of a cluster compute one M = 256 tile; each holds its 128 rows of A (shared memory or
+    TMEM) and of D and half of B's rows (the layout the 2-CTA variant of the chains would use)."""
+    torch.manual_seed(n + 3 * k + ts)
+    lib = tn._lib.load()
+    a = torch.randn(256, k, device="cuda").bfloat16()
+    b = torch.randn(n, k, device="cuda").bfloat16()
+    d = torch.zeros(256, n, device="cuda")
+    vp = tn._lib.c_void_p
+    tn._lib.check(lib.nerf_selftest_umma2(vp(a.data_ptr()), vp(b.data_ptr()), tn._lib.ptr(d), n, k, ts, 1, 0, None,
+                                          tn._lib.stream()), "umma2")
+    torch.cuda.synchronize()
+    torch.testing.assert_close(d, a.float() @ b.float().t(), rtol=1e-4, atol=1e-3)

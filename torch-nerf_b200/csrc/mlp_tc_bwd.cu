@@ -204,30 +204,49 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
       __syncwarp();
     };
 
+    // head gradients and the h9 ReLU masks of this thread's row of a tile (loaded one tile ahead)
+    struct HeadIn {
+      float gz0, gz1, gz2, gsp;
+      uint32_t mk[2];
+    } nx;
+    auto load_heads = [&](int64_t tile_) {
+      nx.gz0 = nx.gz1 = nx.gz2 = nx.gsp = 0.f;
+      nx.mk[0] = nx.mk[1] = 0u;
+      const int64_t grow_ = tile_ * kTileM + row;
+      if (tile_ < ntiles) {
+        const uint32_t* mrow =
+            reinterpret_cast<const uint32_t*>(a.cache + cache_mask_offset(a.m) + (size_t)tile_ * kMaskTileBytes) + row;
+        nx.mk[0] = __ldg(mrow + (64 + 2 * blk) * kTileM);
+        nx.mk[1] = __ldg(mrow + (64 + 2 * blk + 1) * kTileM);
+        if (grow_ < a.m) {
+          const float r0 = __ldg(a.rgb + 3 * grow_), r1 = __ldg(a.rgb + 3 * grow_ + 1), r2 = __ldg(a.rgb + 3 * grow_ + 2);
+          nx.gz0 = __ldg(a.g_rgb + 3 * grow_) * r0 * (1.f - r0);
+          nx.gz1 = __ldg(a.g_rgb + 3 * grow_ + 1) * r1 * (1.f - r1);
+          nx.gz2 = __ldg(a.g_rgb + 3 * grow_ + 2) * r2 * (1.f - r2);
+          const uint32_t smask = __ldg(mrow + kMaskSigmaWord * kTileM);
+          nx.gsp = (smask & 1u) ? __ldg(a.g_sigma + grow_) : 0.f;
+        }
+      }
+    };
+    load_heads(2 * (int64_t)blockIdx.x + slot);
+
     for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
       const int64_t tile = 2 * pair + slot;
       const bool valid = tile < ntiles;
-      const int64_t grow = tile * kTileM + row;
       uint8_t* g_tile = a.scratch + (size_t)tile * kGradTileBytes;
       const uint32_t* mask_row =
           reinterpret_cast<const uint32_t*>(a.cache + cache_mask_offset(a.m) + (size_t)tile * kMaskTileBytes) + row;
       // ---- input stage: heads on CUDA cores: gz = g_rgb * rgb (1 - rgb) (sigmoid backward),
-      //      g_sigma_pre = g_sigma * (sigma_pre > 0); G9 = (gz . W_out) masked by h9 > 0 into TMEM
-      float gz0 = 0.f, gz1 = 0.f, gz2 = 0.f, gsp = 0.f;
-      if (grow < a.m) {
-        const float r0 = __ldg(a.rgb + 3 * grow), r1 = __ldg(a.rgb + 3 * grow + 1), r2 = __ldg(a.rgb + 3 * grow + 2);
-        gz0 = __ldg(a.g_rgb + 3 * grow) * r0 * (1.f - r0);
-        gz1 = __ldg(a.g_rgb + 3 * grow + 1) * r1 * (1.f - r1);
-        gz2 = __ldg(a.g_rgb + 3 * grow + 2) * r2 * (1.f - r2);
-        const uint32_t smask = __ldg(mask_row + kMaskSigmaWord * kTileM);
-        gsp = (smask & 1u) ? __ldg(a.g_sigma + grow) : 0.f;
-      }
+      //      g_sigma_pre = g_sigma * (sigma_pre > 0); G9 = (gz . W_out) masked by h9 > 0 into TMEM.
+      //      (the loads were issued during the previous tile's last layers)
+      const float gz0 = nx.gz0, gz1 = nx.gz1, gz2 = nx.gz2, gsp = nx.gsp;
+      const uint32_t mk9[2] = {nx.mk[0], nx.mk[1]};
       if (blk == 0 && valid) ghead_out[tile * kTileM + row] = make_float4(gz0, gz1, gz2, gsp);
       staging_free();
 #pragma unroll
       for (int gi = 0; gi < 2; ++gi) {
         const int col0 = 64 * blk + 32 * gi;
-        const uint32_t mk = valid ? __ldg(mask_row + (64 + 2 * blk + gi) * kTileM) : 0u;
+        const uint32_t mk = mk9[gi];
         float f[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -249,6 +268,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
       uint32_t wh[2][16];  // bf16 pairs of N-half 0, held until half 1's MMAs have stopped reading the G operand
 #pragma unroll 1
       for (int j = 0; j < kNumBwdLayers; ++j) {
+        if (j == kNumBwdLayers - 2) load_heads(2 * (pair + gridDim.x) + slot);  // in flight during the last two layers
         const int slot_m = 8 - j;  // ReLU mask of the layer output this gradient flows into (j >= 1): h7 .. h0
         // sign-bit masks of this thread's four 32-column groups (0 = every column passes: layer j = 0 has no ReLU)
         uint32_t mk[4] = {0u, 0u, 0u, 0u};
