@@ -319,6 +319,58 @@ def run_b200(args):
                   "tensor_frac_sustained": flop_frame / (frame_ms * 1e-3) / 1e12 / pk["tf_sustained"],
                   "finite": bool(torch.isfinite(img).all().item())}
 
+    # ---- HBM-bound stages: ray generation, sampling, compositing at the frame's ray count, each kernel timed
+    #      alone with CUDA events; algorithmic bytes per unit as listed in DESIGN.md section 4
+    stages = None
+    if rank == 0 and args.precision == "bf16":
+        lib = tn._lib.load()
+        P, st = tn._lib.ptr, tn._lib.stream
+        nr = IMG * IMG
+        S = SC + SF
+        cam_s = cams[0].pack(False)
+        ro = torch.empty(nr, 3, device=dev); rd = torch.empty(nr, 3, device=dev)
+        u_c = torch.rand(nr, SC, device=dev); u1 = torch.rand(nr, SF, device=dev); u2 = torch.rand(nr, SF, device=dev)
+        w_c = torch.rand(nr, SC, device=dev)
+        t_c = torch.empty(nr, SC, device=dev); d_c = torch.empty(nr, SC, device=dev)
+        t_f = torch.empty(nr, S, device=dev); d_f = torch.empty(nr, S, device=dev)
+        sig = torch.rand(nr, S, device=dev); rad = torch.rand(nr, S, 3, device=dev)
+        rgb_o = torch.empty(nr, 3, device=dev); w_o = torch.empty(nr, S, device=dev)
+        g_rgb = torch.rand(nr, 3, device=dev); g_sig = torch.empty(nr, S, device=dev); g_rad = torch.empty(nr, S, 3, device=dev)
+
+        def timed(fn, reps=5):
+            for _ in range(2):
+                fn()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            ev0.record()
+            for _ in range(reps):
+                fn()
+            ev1.record()
+            torch.cuda.synchronize()
+            return ev0.elapsed_time(ev1) * 1e-3 / reps
+
+        ck = tn._lib.check
+        runs = [
+            ("raygen_kernel", nr * 24,
+             lambda: ck(lib.nerf_generate_rays_from_pixels(None, 0, nr, cam_s, P(ro), P(rd), st()), "raygen")),
+            ("sample_coarse_kernel", nr * SC * 12,
+             lambda: ck(lib.nerf_sample_coarse(P(ro), P(rd), nr, SC, 2.0, 6.0, P(u_c), P(t_c), None, None, P(d_c), st()), "coarse")),
+            ("sample_fine_kernel", nr * (SC * 8 + SF * 8 + S * 8),
+             lambda: ck(lib.nerf_sample_fine(P(ro), P(rd), nr, SC, SF, 2.0, 6.0, P(w_c), P(u_c), P(u1), P(u2), None, P(t_f), None,
+                                             None, P(d_f), st()), "fine")),
+            ("composite_fwd_kernel", nr * S * 24 + nr * 12,
+             lambda: ck(lib.nerf_composite_fwd(P(sig), P(rad), P(d_f), None, nr, S, P(rgb_o), P(w_o), None, None, st()), "comp")),
+            ("composite_bwd_kernel", nr * S * 36 + nr * 12,
+             lambda: ck(lib.nerf_composite_bwd(P(sig), P(rad), P(d_f), P(g_rgb), None, nr, S, P(g_sig), P(g_rad), st()), "compb")),
+        ]
+        stages = []
+        for name, nbytes, fn in runs:
+            sec = timed(fn)
+            stages.append({"kernel": name, "rays": nr, "bound": "hbm", "algorithmic_bytes": nbytes, "launch_ms": sec * 1e3,
+                           "achieved": nbytes / sec / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                           "frac": nbytes / sec / 1e9 / pk["hbm_gbs"]})
+        del ro, rd, u_c, u1, u2, w_c, t_c, d_c, t_f, d_f, sig, rad, rgb_o, w_o, g_rgb, g_sig, g_rad
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -339,7 +391,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks,
             "step_tensor_frac_sustained": step_flop / (ms_dev / args.steps * 1e-3) / 1e12 / pk["tf_sustained"],
-            "roofline": roof, "roofline_mlp": roof_mlp, "cpu_baseline": cpu, "render": render,
+            "roofline": roof, "roofline_mlp": roof_mlp, "roofline_stages": stages, "cpu_baseline": cpu, "render": render,
             "loss_last": [float(x) for x in losses_host[total_steps - 1]],
         }
         print(json.dumps(line))
