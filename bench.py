@@ -58,15 +58,41 @@ def blender_focal(w, angle=0.6911112070083618):
 
 
 class ClockSampler:
-    """Samples SM clocks / throttle reasons with nvidia-smi during the timed region."""
+    """Samples SM clocks / throttle reasons during the timed region: NVML every 10 ms when pynvml is importable
+    (nvidia_ml_py), else one nvidia-smi query every 200 ms."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index):
         self.idx, self.samples, self._stop, self._th = gpu_index, [], threading.Event(), None
+        self.source = "nvidia-smi"
+
+    def _run_nvml(self):
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[self.idx]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.idx
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        self.source = "nvml"
+        while not self._stop.is_set():
+            mask = int(reasons_fn(h))
+            row = [str(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))), str(mx)]
+            row += ["Active" if mask & self.BITS[n] else "Not Active" for n in self.NAMES]
+            self.samples.append(row)
+            self._stop.wait(0.01)
 
     def _run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:
+            self.source = "nvidia-smi"
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
@@ -91,10 +117,10 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
         mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.samples)}
+        reasons = [n for i, n in enumerate(self.NAMES)
+                   if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.samples), "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline (oracle port)
