@@ -187,7 +187,9 @@ int nerf_selftest_umma(const uint16_t* a_dev, const uint16_t* b_dev, float* d_de
 /* debugging aid: when buf_dev != NULL, CTA 0 of the next nerf_mlp_bf16_forward launches records, for its first
  * `tiles` tiles and every layer, 8 values into buf_dev[(tile*10 + layer)*8 + k]: SM-clock stamps k=0 MMA layer
  * start, 1 MMA layer issued, 2 accumulator seen by the epilogue, 3 epilogue done; cycle sums k=4 MMA thread waiting
- * for activations, 5 waiting for weights.  Pass NULL to switch it off. */
+ * for activations, 5 waiting for weights.  Pass NULL to switch it off.  Bits 16+ of `tiles` select a debug store mode
+ * of the training-mode forward (0 normal, 1 skip the cache block stores, 2 wrap them onto an L2-resident window): timing
+ * experiments only, the results of modes 1 and 2 are unusable. */
 int nerf_debug_set_profile_buffer(unsigned long long* buf_dev, int tiles);
 
 /* profiling aid: selects which phases nerf_mlp_bf16_backward runs (bit 0 zero gradients, bit 1 dgrad chain, bit 2 wgrad;
