@@ -10,11 +10,13 @@ from .ray_samplers import RayBundle, RaySamplerBase, StratifiedSampler, make_bin
 from .scene import PrimitiveBase, PrimitiveCube
 from .signal_encoder import PositionalEncoder, SignalEncoderBase
 from .volume_renderer import VolumeRenderer
-from . import checkpoint
+from . import checkpoint, datasets
+from .datasets import BlenderDataset, LLFFDataset
 from .trainer import Trainer, center_crop_pixel_indices, exp_lr_gamma
 
 __all__ = [
     "PerspectiveCamera", "IntegratorBase", "QuadratureIntegrator", "NeRF", "RayBundle", "RaySamplerBase",
     "StratifiedSampler", "make_bins", "sample_pdf", "PrimitiveBase", "PrimitiveCube", "PositionalEncoder",
-    "SignalEncoderBase", "VolumeRenderer", "Trainer", "checkpoint", "center_crop_pixel_indices", "exp_lr_gamma",
+    "SignalEncoderBase", "VolumeRenderer", "Trainer", "checkpoint", "datasets",
+    "BlenderDataset", "LLFFDataset", "center_crop_pixel_indices", "exp_lr_gamma",
 ]
