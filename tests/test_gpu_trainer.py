@@ -77,3 +77,23 @@ def test_render_image_and_validate(tn, tmp_path):
     from PIL import Image
 
     assert np.asarray(Image.open(tmp_path / "00000.png")).shape == (h, w, 3)
+
+
+def test_train_from_blender_fixture(tn):
+    """Rows f1 + f4 together: the Blender reader feeds Trainer.train_one_epoch exactly like the reference's DataLoader
+    feeds train.py (batch size 1: (H, W, 3) image + (4, 4) pose)."""
+    import os
+
+    from torch_nerf_b200.trainer import Trainer
+
+    data = tn.BlenderDataset(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "data", "blender"), "lego",
+                             "train", half_res=False, white_bg=True)
+    torch.manual_seed(0)
+    c, f = tn.NeRF(63, 27, precision="bf16").cuda(), tn.NeRF(63, 27, precision="bf16").cuda()
+    tr = Trainer(c, f, num_pixels=48, num_iter=100)
+    intr = {"f_x": data.focal_length, "f_y": data.focal_length, "img_width": data.img_width, "img_height": data.img_height}
+    loader = torch.utils.data.DataLoader(data, batch_size=1, shuffle=False)
+    for epoch in (0, 10):  # centre-crop warm-up (12 candidate pixels < 48: all of them), then whole-frame draws
+        out = tr.train_one_epoch(loader, intr, epoch)
+        assert np.isfinite([out["coarse_loss"], out["fine_loss"], out["loss"]]).all()
+        assert 0.0 < out["loss"] < 2.0
