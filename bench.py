@@ -327,23 +327,37 @@ def run_b200(args):
                                  "measures 6.7 TB/s on the same pool (tools/prof_store.py), hence frac slightly above 1",
                     "launch_ms": sec_w * 1e3}
             del cache, scratch
-        # ---- full 800x800 frame (configs[2])
+    # ---- full 800x800 frame (configs[2]): every rank renders its contiguous share of the pixels (no collective in the
+    #      data path); the frame time is the slowest rank's, measured with CUDA events between barriers
+    if args.precision == "bf16" or rank == 0:
+        from torch_nerf_b200.parallel import shard_range
+
         cam = cams[0]
+        lo, hi = shard_range(IMG * IMG, rank, world) if args.precision == "bf16" else (0, IMG * IMG)
         for _ in range(2):
-            eng_render.render_frame(cam)
+            eng_render.render_frame(cam, False, lo, hi - lo)
         torch.cuda.synchronize()
+        if world > 1 and args.precision == "bf16":
+            dist.barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 3
         ev0.record()
         for _ in range(reps):
-            img = eng_render.render_frame(cam)
+            img = eng_render.render_frame(cam, False, lo, hi - lo)
         ev1.record()
         torch.cuda.synchronize()
         frame_ms = ev0.elapsed_time(ev1) / reps
+        if world > 1 and args.precision == "bf16":
+            tmax = torch.tensor([frame_ms], device=dev)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            frame_ms = float(tmax.item())
         flop_frame = IMG * IMG * (SC + SC + SF) * FLOP_FWD_PER_EVAL
-        render = {"frame_ms_1gpu": frame_ms, "resolution": [IMG, IMG], "rays_per_s": IMG * IMG / (frame_ms * 1e-3),
-                  "tensor_frac_sustained": flop_frame / (frame_ms * 1e-3) / 1e12 / pk["tf_sustained"],
+        sharded = world if args.precision == "bf16" else 1
+        render = {"frame_ms": frame_ms, "n_gpus": sharded, "resolution": [IMG, IMG], "rays_per_s": IMG * IMG / (frame_ms * 1e-3),
+                  "tensor_frac_sustained": flop_frame / (frame_ms * 1e-3) / 1e12 / (pk["tf_sustained"] * sharded),
                   "finite": bool(torch.isfinite(img).all().item())}
+        if sharded == 1:
+            render["frame_ms_1gpu"] = frame_ms
 
     # ---- HBM-bound stages: ray generation, sampling, compositing at the frame's ray count, each kernel timed
     #      alone with CUDA events; algorithmic bytes per unit as listed in DESIGN.md section 4
