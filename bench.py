@@ -196,7 +196,10 @@ def run_b200(args):
     eng_render = eng if args.precision == "bf16" else HotPathEngine(coarse, fine, SC, SF, precision="bf16")
     # runner_utils.py:690-711: Adam(lr 5e-4, eps 1e-8), ExponentialLR gamma = (5e-5/5e-4)^(1/300000); one Adam over both
     # networks' parameters -- here as ONE flat parameter that all 44 tensors alias (elementwise-identical update)
-    opt = torch.optim.Adam([flat.param], lr=5e-4, eps=1e-8, fused=True)
+    from torch_nerf_b200.optim import FlatAdam
+
+    opt = FlatAdam([flat.param], lr=5e-4, eps=1e-8)  # torch.optim.Adam's state and math, one kernel launch (csrc/optim.cu)
+    opt.grad_scale = 1.0 / world
     sched = torch.optim.lr_scheduler.ExponentialLR(opt, (5e-5 / 5e-4) ** (1.0 / 300000))
     torch.manual_seed(1234 + rank)  # per-rank uniform stream / pixels
     focal = blender_focal(IMG)
@@ -222,7 +225,7 @@ def run_b200(args):
         else:
             pix, tgt = dev_pix[i], dev_tgt[i]
         eng.train_pixels(cam, pix, tgt, False, loss_out=losses_dev)
-        allreduce_mean_(flat.grad, world)  # one NCCL all-reduce of the 4.77 MB flat gradient buffer
+        allreduce_mean_(flat.grad, world, scale=False)  # one NCCL all-reduce (sum) of the 4.77 MB flat gradient buffer
         opt.step()
         sched.step()
         if e2e:
@@ -250,7 +253,7 @@ def run_b200(args):
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, eng.launches - l0
+        return ms, eng.launches - l0 + (total_steps - args.warmup)  # + one Adam launch per step
 
     with ClockSampler(local) as clk:
         ms_dev, launches = timed(False)

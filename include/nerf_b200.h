@@ -122,6 +122,14 @@ int nerf_composite_bwd(const float* sigma_dev, const float* radiance_dev, const 
                        const float* g_rgb_dev, const float* g_w_dev, int64_t n, int s, float* g_sigma_dev,
                        float* g_radiance_dev, nerf_stream_t stream);
 
+/* Adam update of a flat fp32 parameter buffer (torch.optim.Adam as set up at runners/runner_utils.py:691-695: lr, eps
+ * given; betas, weight_decay = 0, amsgrad = False defaults), update number `step` (1-based):
+ *   g = grad * grad_scale;  m += (1 - beta1)(g - m);  v = beta2 v + (1 - beta2) g^2;
+ *   p -= lr / (1 - beta1^step) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps)
+ * grad_scale folds the 1/world of the data-parallel gradient average into the same pass.  Buffers 16-byte aligned. */
+int nerf_adam_step(float* param_dev, const float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t n, double lr,
+                   double beta1, double beta2, double eps, int64_t step, double grad_scale, nerf_stream_t stream);
+
 /* MSE loss head of one render pass (runners/runner_utils.py:731 nn.MSELoss as used at runners/train.py:180,202):
  * *loss_accum_dev += mean((rgb - target)^2) over the N*3 elements; g_rgb = 2/(3N) (rgb - target). */
 int nerf_mse_loss(const float* rgb_dev, const float* target_dev, int64_t n, float* g_rgb_dev,

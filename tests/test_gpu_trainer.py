@@ -97,3 +97,32 @@ def test_train_from_blender_fixture(tn):
         out = tr.train_one_epoch(loader, intr, epoch)
         assert np.isfinite([out["coarse_loss"], out["fine_loss"], out["loss"]]).all()
         assert 0.0 < out["loss"] < 2.0
+
+
+def test_flat_adam_matches_torch_adam_and_oracle(tn):
+    """optim.FlatAdam (one launch, csrc/optim.cu) against torch.optim.Adam and the numpy restatement, incl. the folded
+    1/world gradient scale and a learning-rate schedule."""
+    from torch_nerf_b200.optim import FlatAdam
+
+    torch.manual_seed(0)
+    n = 1191688  # both networks
+    p0 = torch.randn(n, device="cuda") * 0.1
+    a = torch.nn.Parameter(p0.clone()); b = torch.nn.Parameter(p0.clone())
+    ours, ref = FlatAdam([a], lr=5e-4, eps=1e-8), torch.optim.Adam([b], lr=5e-4, eps=1e-8)
+    s_ours = torch.optim.lr_scheduler.ExponentialLR(ours, 0.9)
+    s_ref = torch.optim.lr_scheduler.ExponentialLR(ref, 0.9)
+    ours.grad_scale = 0.25
+    p_np, m_np, v_np = p0.cpu().numpy(), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    for step in range(1, 5):
+        g = torch.randn(n, device="cuda") * 1e-3
+        a.grad = g.clone(); b.grad = g * 0.25
+        lr = ours.param_groups[0]["lr"]
+        ours.step(); ref.step(); s_ours.step(); s_ref.step()
+        p_np, m_np, v_np = orc.adam_step(p_np, (g * 0.25).cpu().numpy(), m_np, v_np, step, lr)
+        torch.testing.assert_close(a.data, b.data, rtol=0, atol=2e-7)
+        np.testing.assert_allclose(a.data.cpu().numpy(), p_np, rtol=0, atol=2e-7)
+    sd = ours.state_dict()
+    assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"} and float(sd["state"][0]["step"]) == 4.0
+    ref2 = torch.optim.Adam([torch.nn.Parameter(p0.clone())], lr=1.0)
+    ref2.load_state_dict(sd)  # torch.optim.Adam accepts the state as is
+    assert ref2.param_groups[0]["lr"] == pytest.approx(5e-4 * 0.9 ** 4)

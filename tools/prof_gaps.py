@@ -11,7 +11,8 @@ torch.manual_seed(0)
 c = tn.NeRF(63, 27, precision="bf16").cuda(); f = tn.NeRF(63, 27, precision="bf16").cuda()
 eng = HotPathEngine(c, f, 64, 128, "bf16")
 flat = eng.enable_flat_params()
-opt = torch.optim.Adam([flat.param], lr=5e-4, fused=True)
+from torch_nerf_b200.optim import FlatAdam
+opt = FlatAdam([flat.param], lr=5e-4)
 focal = bench.blender_focal(800)
 cam = tn.PerspectiveCamera({"f_x": focal, "f_y": focal, "img_width": 800, "img_height": 800}, bench.pose_spherical(30., -30., 4.), 2.0, 6.0)
 pix = torch.randperm(800 * 800)[:4096].cuda()

@@ -12,11 +12,12 @@ from .signal_encoder import PositionalEncoder, SignalEncoderBase
 from .volume_renderer import VolumeRenderer
 from . import checkpoint, datasets
 from .datasets import BlenderDataset, LLFFDataset
+from .optim import FlatAdam
 from .trainer import Trainer, center_crop_pixel_indices, exp_lr_gamma
 
 __all__ = [
     "PerspectiveCamera", "IntegratorBase", "QuadratureIntegrator", "NeRF", "RayBundle", "RaySamplerBase",
     "StratifiedSampler", "make_bins", "sample_pdf", "PrimitiveBase", "PrimitiveCube", "PositionalEncoder",
-    "SignalEncoderBase", "VolumeRenderer", "Trainer", "checkpoint", "datasets",
+    "SignalEncoderBase", "VolumeRenderer", "Trainer", "FlatAdam", "checkpoint", "datasets",
     "BlenderDataset", "LLFFDataset", "center_crop_pixel_indices", "exp_lr_gamma",
 ]

@@ -16,7 +16,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIB_DIR, "libnerf_b200.so")
 SOURCES = ["api.cu", "rays.cu", "encode_composite.cu", "mlp_f32.cu", "mlp_tc_pack.cu", "mlp_tc_fwd.cu", "mlp_tc_bwd.cu",
-           "mlp_tc_selftest.cu"]
+           "mlp_tc_selftest.cu", "optim.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,

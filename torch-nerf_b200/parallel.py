@@ -44,13 +44,15 @@ def shard_rays(pixel_indices: torch.Tensor, target: torch.Tensor, rank: int, wor
     return pixel_indices[a:b], target[a:b]
 
 
-def allreduce_mean_(flat_grad: torch.Tensor, world: int | None = None) -> torch.Tensor:
-    """In-place average of the flat gradient buffer over all ranks (sum all-reduce, then scale)."""
+def allreduce_mean_(flat_grad: torch.Tensor, world: int | None = None, scale: bool = True) -> torch.Tensor:
+    """In-place average of the flat gradient buffer over all ranks (sum all-reduce, then scale).  With scale=False
+    only the sum is formed: optim.FlatAdam folds the 1/world into its update (grad_scale)."""
     if not (dist.is_available() and dist.is_initialized()):
         return flat_grad
     world = dist.get_world_size() if world is None else world
     if world == 1:
         return flat_grad
     dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
-    flat_grad.mul_(1.0 / world)
+    if scale:
+        flat_grad.mul_(1.0 / world)
     return flat_grad

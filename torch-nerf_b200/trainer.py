@@ -5,7 +5,7 @@ render / validation step, restated over the fused engine.
     optimizer setup   ref runners/runner_utils.py:663-717
     render_image      ref runners/runner_utils.py:834-918, runners/train.py:296-341 (clamp, (H*W,3) -> (3,H,W), PNG)
 
-Differences that are deliberate: both networks live in one flat buffer stepped by ONE fused Adam launch; the loss is
+Differences that are deliberate: both networks live in one flat buffer stepped by ONE Adam launch (optim.FlatAdam); the loss is
 accumulated on the device and read back once per epoch (the reference calls .item() three times per iteration); with
 several ranks every rank trains its shard of the pixel batch and the flat gradient is all-reduced once per step.
 A profile of the captured step (tools/prof_gaps.py) shows 17 us of GPU idle time per 5 ms step, so the step is NOT
@@ -66,7 +66,10 @@ class Trainer:
         self.num_pixels = int(num_pixels)
         self.t_near, self.t_far, self.project_to_ndc = float(t_near), float(t_far), bool(project_to_ndc)
         self.rank, self.world = int(rank), int(world)
-        self.optimizer = torch.optim.Adam([self.flat.param], lr=init_lr, eps=eps, fused=True)
+        from .optim import FlatAdam
+
+        self.optimizer = FlatAdam([self.flat.param], lr=init_lr, eps=eps)  # torch.optim.Adam's state layout, one launch
+        self.optimizer.grad_scale = 1.0 / self.world
         self.scheduler = torch.optim.lr_scheduler.ExponentialLR(self.optimizer, exp_lr_gamma(init_lr, end_lr, num_iter))
         self.device = self.engine.device
         # pixel selection is host-side in the reference (np.random.choice / torch.randperm on CPU): one generator,
@@ -93,7 +96,7 @@ class Trainer:
         tgt = pixel_gt.reshape(-1, 3)[pix.to(pixel_gt.device)].to(self.device, torch.float32, non_blocking=True).contiguous()
         losses = self.engine.train_pixels(camera, pix.to(self.device, non_blocking=True), tgt, self.project_to_ndc,
                                           loss_out=self._losses)
-        allreduce_mean_(self.flat.grad, self.world)
+        allreduce_mean_(self.flat.grad, self.world, scale=False)  # the 1/world rides on the Adam kernel
         self.optimizer.step()
         self.scheduler.step()
         return losses
