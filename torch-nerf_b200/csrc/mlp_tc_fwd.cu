@@ -250,17 +250,21 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
     const bool leader = elect_one();
     uint32_t g = 0;
     for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-      const uint8_t* src = a.packed + kPackedFwdOff;
-      for (int c = 0; c < kFwdChunks; ++c) {
-        const uint32_t s = g % kStages, ph = (g / kStages) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        if (leader) {
-          mbar_arrive_expect_tx(&full[s], kChunkBytes);
-          bulk_g2s(sW + s * kChunkBytes, src, kChunkBytes, &full[s]);
+      int chunk0 = 0;  // first chunk of layer l in the packed order (fwd_layer_chunk0)
+      for (int l = 0; l < kNumFwdLayers; chunk0 += fwd_nk(l) * fwd_nh(l), ++l) {
+        for (int h = 0; h < fwd_nh(l); ++h) {
+          for (int kb = 0; kb < fwd_nk(l); ++kb) {  // consumption order of the issuers
+            const uint8_t* src = a.packed + kPackedFwdOff + (size_t)(chunk0 + kb * fwd_nh(l) + h) * kChunkBytes;
+            const uint32_t s = g % kStages, ph = (g / kStages) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            if (leader) {
+              mbar_arrive_expect_tx(&full[s], kChunkBytes);
+              bulk_g2s(sW + s * kChunkBytes, src, kChunkBytes, &full[s]);
+            }
+            __syncwarp();
+            ++g;
+          }
         }
-        __syncwarp();
-        src += kChunkBytes;
-        ++g;
       }
     }
   } else if (warp == 1 || warp == kMmaWarpB) {

@@ -32,6 +32,13 @@ constexpr int kNumFwdLayers = 10;
 __host__ __device__ constexpr int fwd_nk(int l) { return l == 0 ? 1 : ((l == 5 || l == 9) ? 5 : 4); }
 __host__ __device__ constexpr int fwd_nh(int l) { return l == 9 ? 1 : 2; }  // N-halves (fc_9 is 128 wide)
 constexpr int kFwdChunks = 2 * (1 + 4 * 4 + 5 + 3 * 4) + 5;  // 73
+// packed order: per layer, per K chunk, per N-half (the halves of one K chunk are adjacent: together one 256-row operand)
+__host__ __device__ constexpr int fwd_layer_chunk0(int l) {
+  int c = 0;
+  for (int i = 0; i < l; ++i) c += fwd_nk(i) * fwd_nh(i);
+  return c;
+}
+__host__ __device__ constexpr int fwd_chunk_index(int l, int h, int kb) { return fwd_layer_chunk0(l) + kb * fwd_nh(l) + h; }
 constexpr size_t kFwdWeightBytes = (size_t)kFwdChunks * kChunkBytes;
 
 // Order in which the chains visit the four activation k-blocks.  The epilogue's column half h owns blocks {h, h+2}

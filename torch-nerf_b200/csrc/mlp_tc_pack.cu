@@ -1,6 +1,8 @@
 // Weight packing for the tensor-core chains: fp32 (out,in) nn.Linear weights (network/nerf.py:49-59) -> bf16
 // 128B-swizzled K-major chunks (N rows x 64 K-columns) in exactly the order the forward and dgrad chains stream
 // them, plus the fp32 constants the epilogues need.  Re-run after every optimizer step (2.3 MB written).
+#include <initializer_list>
+
 #include "common.cuh"
 #include "mlp_tc_layout.cuh"
 #include "tc_common.cuh"
@@ -67,24 +69,22 @@ static int build_pack_table(PackChunk* t) {
     t[n++] = PackChunk{param, row0, col0, ld, nrows, valid, transpose, off};
     off += (uint32_t)nrows * 128u;
   };
-  // ---- forward chain: per layer, per N-half, per K chunk (consumption order); chunks are 128 rows
-  auto fwd_layer = [&](int param, int row0, int ld, int nh_count, auto&& cols) {
-    for (int nh = 0; nh < nh_count; ++nh) cols(param, row0 + 128 * nh, ld);
+  // ---- forward chain: per layer, per K chunk, per N-half; chunks are 128 output rows x 64 K-columns.  The two N-halves
+  //      of one K chunk are adjacent, so the 32 KB pair is also ONE K-major operand of 256 rows (the inference
+  //      chain's N = 256 MMAs); the training chain fetches the 16 KB halves separately (fwd_chunk_index).
+  struct KCols {
+    int col0, valid;
   };
-  fwd_layer(W_IN, 0, kP, 2, [&](int p, int r, int ld) { add(p, r, 0, ld, 128, kP, 0); });
-  for (int l = 1; l <= 4; ++l)
-    fwd_layer(2 * l, 0, kF, 2, [&](int p, int r, int ld) { for (int kb = 0; kb < 4; ++kb) add(p, r, 64 * kb, ld, 128, 64, 0); });
-  fwd_layer(W_5, 0, kP + kF, 2, [&](int p, int r, int ld) {
-    add(p, r, 0, ld, 128, kP, 0);                                                 // position columns
-    for (int kb = 0; kb < 4; ++kb) add(p, r, kP + 64 * kb, ld, 128, 64, 0);       // h4 columns
-  });
-  for (int l = 6; l <= 7; ++l)
-    fwd_layer(2 * l, 0, kF, 2, [&](int p, int r, int ld) { for (int kb = 0; kb < 4; ++kb) add(p, r, 64 * kb, ld, 128, 64, 0); });
-  fwd_layer(W_8, 1, kF, 2, [&](int p, int r, int ld) { for (int kb = 0; kb < 4; ++kb) add(p, r, 64 * kb, ld, 128, 64, 0); });  // rows 1..256
-  fwd_layer(W_9, 0, kF + kV, 1, [&](int p, int r, int ld) {
-    for (int kb = 0; kb < 4; ++kb) add(p, r, 64 * kb, ld, 128, 64, 0);            // feature columns
-    add(p, r, kF, ld, 128, kV, 0);                                                // view columns
-  });
+  auto fwd_layer = [&](int param, int row0, int ld, int nh_count, std::initializer_list<KCols> ks) {
+    for (const KCols& k : ks)
+      for (int nh = 0; nh < nh_count; ++nh) add(param, row0 + 128 * nh, k.col0, ld, 128, k.valid, 0);
+  };
+  fwd_layer(W_IN, 0, kP, 2, {{0, kP}});
+  for (int l = 1; l <= 4; ++l) fwd_layer(2 * l, 0, kF, 2, {{0, 64}, {64, 64}, {128, 64}, {192, 64}});
+  fwd_layer(W_5, 0, kP + kF, 2, {{0, kP}, {kP, 64}, {kP + 64, 64}, {kP + 128, 64}, {kP + 192, 64}});  // position columns, then h4
+  for (int l = 6; l <= 7; ++l) fwd_layer(2 * l, 0, kF, 2, {{0, 64}, {64, 64}, {128, 64}, {192, 64}});
+  fwd_layer(W_8, 1, kF, 2, {{0, 64}, {64, 64}, {128, 64}, {192, 64}});                                   // rows 1..256
+  fwd_layer(W_9, 0, kF + kV, 1, {{0, 64}, {64, 64}, {128, 64}, {192, 64}, {kF, kV}});                    // features, then view columns
   // ---- dgrad chain: dst(n = input feature, k = output feature); per layer, per N-half of the INPUT features
   off = (uint32_t)kPackedBwdOff;
   auto bwd_layer = [&](int param, int out_row0, int in_col0, int ld, int nk) {
