@@ -255,7 +255,10 @@ __global__ void __launch_bounds__(640, 1) mma_rate_kernel(int iters, int n, int 
     const long long t0 = clock64();
     const int m = mode & 1;
     for (int it = 0; it < iters; ++it) {
-      if (mode & 4) mbar_wait(&bar2[1], 0);  // probe an already-completed barrier before every group
+      if (mode & 4) {  // probe an already-completed barrier before every group (mode bit 6: with test_wait)
+        if (mode & 64) mbar_wait_spin(&bar2[1], 0);
+        else mbar_wait(&bar2[1], 0);
+      }
       if (leader) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -375,7 +378,7 @@ int nerf_selftest_umma2(const uint16_t* a_dev, const uint16_t* b_dev, float* d_d
 
 int nerf_selftest_mma_rate(int blocks, int iters, int n, int mode, int bg_warps, int bg_iters, int bg_store,
                            unsigned long long* cycles_dev, nerf_stream_t stream) {
-  NERF_CHECK_ARG(cycles_dev && blocks > 0 && iters >= 0 && n >= 16 && n <= 256 && n % 16 == 0 && mode >= 0 && mode < 64 &&
+  NERF_CHECK_ARG(cycles_dev && blocks > 0 && iters >= 0 && n >= 16 && n <= 256 && n % 16 == 0 && mode >= 0 && mode < 128 &&
                      bg_warps >= 0 && bg_warps <= 16 && bg_iters >= 0,
                  "nerf_selftest_mma_rate: bad arguments");
   const size_t smem = 16384 + 32768 + 1024;
