@@ -28,6 +28,9 @@ if "--micro" in sys.argv:
     for mode, n in ((1 | 4, 128), (1 | 4 | 64, 128)):
         m, _ = rate(148, 2000, n, mode)
         print(f"mma TS N={n} + probe per 4 with {'test_wait' if mode & 64 else 'try_wait'}: {m:6.1f} cycles/MMA")
+    for mode, n in ((33 | 128, 128), (33 | 128, 256)):
+        m, _ = rate(148, 2000, n, mode)
+        print(f"two issuer warps, ONE accumulator, TS N={n:3d}: {m / 2:6.1f} cycles/MMA aggregate")
     for mode, n in ((33, 128), (33, 64), (32, 128)):
         m, _ = rate(148, 2000, n, mode)
         print(f"two issuer warps, own accumulators, mode={'SS' if (mode & 1) == 0 else 'TS'} N={n:3d}: {m / 2:6.1f} cycles/MMA aggregate ({m:6.1f} per issuer)")

@@ -22,10 +22,14 @@ __global__ void __launch_bounds__(128, 1) selftest_umma_kernel(const uint16_t* _
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = k / 64;
+  const int reps = (variant >> 4) + 1;  // variant 3 only: the whole product is accumulated `reps` times
+  variant &= 15;
+  const bool split = variant == 3;  // two issuing threads accumulate into one accumulator
+  if (split) variant = 2;
   uint8_t* sA;
   uint8_t* sB;
   uint32_t a_blk, b_blk;  // byte stride between 64-column blocks
-  if (variant == 0 || variant == 2) {
+  if (variant == 0 || variant == 2 || variant == 3) {
     a_blk = 128 * 128;
     b_blk = n * 128;
     sA = smem;
@@ -54,7 +58,7 @@ __global__ void __launch_bounds__(128, 1) selftest_umma_kernel(const uint16_t* _
   }
   fence_proxy_async();
   if (threadIdx.x == 0) {
-    mbar_init(&bar, 1);
+    mbar_init(&bar, split ? 2 : 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
@@ -62,6 +66,13 @@ __global__ void __launch_bounds__(128, 1) selftest_umma_kernel(const uint16_t* _
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  if (split) {  // the accumulator starts at zero: every MMA accumulates, so the issue order of the two threads is free
+    uint32_t z[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) z[i] = 0u;
+    for (int c = 0; c < n / 32; ++c) tmem_st32(tmem_base + ((uint32_t)(warp * 32) << 16) + c * 32, z);
+    tmem_st_wait();
+  }
   if (variant == 2) {
     // row = TMEM lane; 64 bf16 (one k-block) = 32 packed words = 32 TMEM columns at [256 + 32*kb, +32)
     const int row = warp * 32 + lane;
@@ -78,7 +89,18 @@ __global__ void __launch_bounds__(128, 1) selftest_umma_kernel(const uint16_t* _
     __syncthreads();
     tc_fence_after();
   }
-  if (threadIdx.x == 0) {
+  if (split) {
+    if ((warp == 0 || warp == 1) && lane == 0) {
+      const uint32_t idesc = make_idesc_bf16((uint32_t)n, false, false);
+      for (int rep = 0; rep < reps; ++rep) {
+        for (int kk = warp; kk < k / 16; kk += 2) {
+          const uint64_t db = desc_kmajor(smem_u32(sB) + (kk / 4) * b_blk + (kk % 4) * 32);
+          umma_bf16_ts(tmem_base, tmem_base + 256 + 8 * kk, db, idesc, 1u);
+        }
+      }
+      umma_commit(&bar);
+    }
+  } else if (threadIdx.x == 0) {
     const uint32_t idesc = make_idesc_bf16((uint32_t)n, variant == 1, variant == 1);
     for (int kk = 0; kk < k / 16; ++kk) {
       uint64_t da, db;
@@ -251,7 +273,7 @@ __global__ void __launch_bounds__(640, 1) mma_rate_kernel(int iters, int n, int 
     const uint64_t da = desc_kmajor(smem_u32(smem));
     const uint64_t db = desc_kmajor(smem_u32(smem) + 16384);
     uint64_t* done = warp == 0 ? &bar : &bar2[0];
-    const uint32_t acc0 = tmem_base + (warp == 1 ? 128u : 0u);
+    const uint32_t acc0 = tmem_base + ((warp == 1 && !(mode & 128)) ? 128u : 0u);  // mode bit 7: both issuers share one accumulator
     const long long t0 = clock64();
     const int m = mode & 1;
     for (int it = 0; it < iters; ++it) {
@@ -354,8 +376,8 @@ int nerf_selftest_write_bw(void* dst_dev, size_t bytes, int mode, int blocks, ne
 int nerf_selftest_umma(const uint16_t* a_dev, const uint16_t* b_dev, float* d_dev, int n, int k, int variant,
                        nerf_stream_t stream) {
   NERF_CHECK_ARG(a_dev && b_dev && d_dev, "nerf_selftest_umma: null pointer");
-  NERF_CHECK_ARG(n >= 64 && n <= 256 && n % 64 == 0 && k >= 64 && k <= 256 && k % 64 == 0 && (variant >= 0 && variant <= 2),
-                 "nerf_selftest_umma: n, k must be multiples of 64 in [64,256]; variant 0|1|2");
+  NERF_CHECK_ARG(n >= 64 && n <= 256 && n % 64 == 0 && k >= 64 && k <= 256 && k % 64 == 0 && (variant >= 0 && (variant & 15) <= 3 && (variant < 16 || (variant & 15) == 3)),
+                 "nerf_selftest_umma: n, k must be multiples of 64 in [64,256]; variant 0|1|2|3");
   size_t smem = (size_t)128 * k * 2 + (size_t)n * k * 2 + 1024;
   NERF_CUDA(cudaFuncSetAttribute(selftest_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   selftest_umma_kernel<<<1, 128, smem, as_stream(stream)>>>(a_dev, b_dev, d_dev, n, k, variant);
@@ -378,7 +400,7 @@ int nerf_selftest_umma2(const uint16_t* a_dev, const uint16_t* b_dev, float* d_d
 
 int nerf_selftest_mma_rate(int blocks, int iters, int n, int mode, int bg_warps, int bg_iters, int bg_store,
                            unsigned long long* cycles_dev, nerf_stream_t stream) {
-  NERF_CHECK_ARG(cycles_dev && blocks > 0 && iters >= 0 && n >= 16 && n <= 256 && n % 16 == 0 && mode >= 0 && mode < 128 &&
+  NERF_CHECK_ARG(cycles_dev && blocks > 0 && iters >= 0 && n >= 16 && n <= 256 && n % 16 == 0 && mode >= 0 && mode < 256 &&
                      bg_warps >= 0 && bg_warps <= 16 && bg_iters >= 0,
                  "nerf_selftest_mma_rate: bad arguments");
   const size_t smem = 16384 + 32768 + 1024;
