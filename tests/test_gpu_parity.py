@@ -143,6 +143,78 @@ def test_fine_sampling_properties_full_size(tn):
     assert torch.equal(pts, ray_o[:, None, :] + t[..., None] * ray_d[:, None, :])
 
 
+@pytest.mark.parametrize("s,near,far", [(64, 2.0, 6.0), (192, 0.0, 1.0), (60, 0.37, 5.13), (7, 2.0, 6.0)])
+def test_coarse_fused_form_equals_materialised_form(tn, s, near, far):
+    """The elementwise kernel behind materialize=False (samples % 4 == 0) and the warp-per-ray kernel must agree bit for
+    bit with each other and, for float32-exact bins, with the oracle."""
+    rng = np.random.default_rng(s)
+    n = 5003
+    o, d = rng.normal(size=(n, 3)).astype(np.float32), rng.normal(size=(n, 3)).astype(np.float32)
+    u = rng.random((n, s), dtype=np.float32)
+    bundle = tn.RayBundle(cu(o), cu(d), near, far, False)
+    sampler = tn.StratifiedSampler()
+    _, _, delta_m, ex_m = sampler.sample_along_rays(bundle, s, device=0, uniforms=(cu(u),), return_extras=True)
+    _, _, delta_f, ex_f = sampler.sample_along_rays(bundle, s, device=0, uniforms=(cu(u),), return_extras=True, materialize=False)
+    assert torch.equal(ex_m["t"], ex_f["t"]) and torch.equal(delta_m, delta_f)
+    _, _, delta_o, t_o = orc.sample_along_rays_coarse(o, d, near, far, s, u)
+    assert np.array_equal(ex_f["t"].cpu().numpy(), t_o) and np.array_equal(delta_f.cpu().numpy(), delta_o)
+
+
+@pytest.mark.parametrize("sc,sf", [(64, 128), (32, 64), (64, 64), (96, 128)])
+@pytest.mark.parametrize("kind", ["peaked", "zeros", "wide"])
+def test_fine_sampling_paths_vs_oracle(tn, sc, sf, kind):
+    """Every fine-sampling path -- the register-sort kernel of the default 64+128, the general shared-memory sort, the
+    warp-scan CDF and its sequential fall-back (`wide`: pdf values below 2^-28) -- against the oracle, bit for bit."""
+    rng = np.random.default_rng(sc * 1000 + sf)
+    n = 2051
+    o, d = rng.normal(size=(n, 3)).astype(np.float32), rng.normal(size=(n, 3)).astype(np.float32)
+    if kind == "peaked":
+        w = (rng.random((n, sc), dtype=np.float32) ** 8).astype(np.float32)
+    elif kind == "zeros":
+        w = np.zeros((n, sc), np.float32)
+        w[::2, sc // 3] = 0.9
+    else:
+        w = np.where(rng.random((n, sc)) < 0.1, 3e4, 1e-7).astype(np.float32)
+    u0, u1, u2 = (rng.random((n, k), dtype=np.float32) for k in (sc, sf, sf))
+    bundle = tn.RayBundle(cu(o), cu(d), 2.0, 6.0, False)
+    w_dev = cu(w)
+    pts, dirs, delta, ex = tn.StratifiedSampler().sample_along_rays(
+        bundle, (sc, sf), device=0, weights=w_dev, uniforms=(cu(u0), cu(u1), cu(u2)), return_extras=True)
+    w_o = w.copy()
+    pts_o, _, delta_o, t_o, idx_o = orc.sample_along_rays_fine(o, d, 2.0, 6.0, sc, sf, w_o, u0, u1, u2)
+    assert np.array_equal(ex["idx"].cpu().numpy(), idx_o), "bin indices must be bit-exact"
+    assert np.array_equal(w_dev.cpu().numpy(), w_o)
+    assert np.array_equal(ex["t"].cpu().numpy(), t_o)
+    assert np.array_equal(delta.cpu().numpy(), delta_o)
+    assert np.array_equal(pts.cpu().numpy(), pts_o)
+    # fused form (no (N,S,3) outputs) gives the same t / delta
+    w_dev2 = cu(w)
+    _, _, delta2, ex2 = tn.StratifiedSampler().sample_along_rays(
+        bundle, (sc, sf), device=0, weights=w_dev2, uniforms=(cu(u0), cu(u1), cu(u2)), return_extras=True, materialize=False)
+    assert torch.equal(ex2["t"], ex["t"]) and torch.equal(delta2, delta)
+
+
+@pytest.mark.parametrize("near,far", [(0.37, 5.13), (0.0, 1.0), (1.7, 93.1)])
+def test_fine_sampling_inexact_bins_vs_oracle(tn, near, far):
+    """Scene bounds whose bin edges are not exact in float32: the stratified draw may come out locally unordered by an
+    ulp, which the 64+128 kernel must detect (it skips the coarse sort otherwise)."""
+    rng = np.random.default_rng(77)
+    n, sc, sf = 4099, 64, 128
+    o, d = rng.normal(size=(n, 3)).astype(np.float32), rng.normal(size=(n, 3)).astype(np.float32)
+    w = (rng.random((n, sc), dtype=np.float32) ** 6).astype(np.float32)
+    u0, u1, u2 = (rng.random((n, k), dtype=np.float32) for k in (sc, sf, sf))
+    u0[::3] = np.float32(1.0) - np.float32(2.0 ** -24)  # draws at the top of every bin: neighbours collide
+    u0[1::3, ::2] = 0.0
+    bundle = tn.RayBundle(cu(o), cu(d), near, far, False)
+    w_dev = cu(w)
+    _, _, delta, ex = tn.StratifiedSampler().sample_along_rays(
+        bundle, (sc, sf), device=0, weights=w_dev, uniforms=(cu(u0), cu(u1), cu(u2)), return_extras=True, materialize=False)
+    _, _, delta_o, t_o, idx_o = orc.sample_along_rays_fine(o, d, near, far, sc, sf, w.copy(), u0, u1, u2)
+    assert np.array_equal(ex["idx"].cpu().numpy(), idx_o)
+    assert np.array_equal(ex["t"].cpu().numpy(), t_o)
+    assert np.array_equal(delta.cpu().numpy(), delta_o)
+
+
 def test_sampler_value_errors(tn):
     bundle = tn.RayBundle(torch.zeros(4, 3, device="cuda"), torch.ones(4, 3, device="cuda"), 2.0, 6.0, False)
     s = tn.StratifiedSampler()
@@ -193,7 +265,7 @@ def test_composite_golden(tn):
     np.testing.assert_allclose(sigma.grad.cpu().numpy(), g["g_sigma_w"], rtol=5e-4, atol=5e-5)
 
 
-@pytest.mark.parametrize("s", [64, 192, 100])
+@pytest.mark.parametrize("s", [64, 192, 100, 33, 256, 300])
 def test_composite_full_size_vs_oracle(tn, s):
     rng = np.random.default_rng(10 + s)
     n = 4096

@@ -149,3 +149,31 @@ def test_train_step_golden():
     np.testing.assert_allclose(out["fine_loss"], float(g["loss_f"]), rtol=1e-4)
     check_digest(out["coarse_grads"], g, prefix="c/", rtol=2e-3, atol=1e-6)
     check_digest(out["fine_grads"], g, prefix="f/", rtol=2e-3, atol=1e-6)
+
+
+def test_cdf_warp_scan_is_exactly_the_sequential_sum():
+    """rays.cu build_cdf replaces torch.cumsum's sequential float64 running sum by a warp scan when every pdf value is
+    in [2^-28, 1].  The claim is that all float64 partial sums are then exact, so the association order cannot matter:
+    replay the kernel's Hillis-Steele scan (32-wide chunks + carry) in numpy and demand bit equality with np.cumsum."""
+    rng = np.random.default_rng(5)
+    for sc in (64, 96, 256):
+        w = (rng.random((4096, sc), dtype=np.float32) ** 8).astype(np.float32)
+        w[::7] = 0.0
+        w += np.float32(1e-5)
+        pdf = (w / orc.torch_cpu_sum_lastdim(w)[:, None]).astype(np.float32)
+        assert pdf.min() >= 2.0 ** -28 and pdf.max() <= 1.0
+        seq = np.cumsum(pdf.astype(np.float64), axis=-1)
+        scan = np.empty_like(seq)
+        carry = np.zeros(pdf.shape[0])
+        for base in range(0, sc, 32):
+            inc = pdf[:, base:base + 32].astype(np.float64)
+            d = 1
+            while d < 32:
+                up = np.zeros_like(inc)
+                up[:, d:] = inc[:, :-d]
+                inc = inc + up
+                d *= 2
+            inc = inc + carry[:, None]
+            scan[:, base:base + 32] = inc
+            carry = inc[:, -1]
+        assert np.array_equal(scan, seq)

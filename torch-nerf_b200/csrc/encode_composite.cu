@@ -246,6 +246,224 @@ __global__ void __launch_bounds__(kCompWarps * 32)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K7 / K8 for rays of at most 32*G samples (G = 2, 4, 6, 8; the reference's 64 and 192 are G = 2 and 6).  Same
+// arithmetic as the chunk-walking kernels above; what changes is the memory schedule: a warp issues EVERY load of its
+// ray (sigma, delta, t, the 3*S radiance floats as consecutive 128-byte rows) before the first dependent instruction,
+// so ~3.8 KB per warp are in flight instead of one 640-byte chunk, and each input is read exactly once (the backward
+// no longer re-reads sigma/delta for its prefix pass).
+// ------------------------------------------------------------------------------------------------
+// inclusive float64 scans of G independent 32-element chunks, interleaved so the G shuffle/add chains overlap
+template <int G>
+__device__ __forceinline__ void chunk_scans_up(double (&inc)[G]) {
+  const int lane = lane_id();
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    double up[G];
+#pragma unroll
+    for (int c = 0; c < G; ++c) up[c] = shfl_up_f64(inc[c], d);
+#pragma unroll
+    for (int c = 0; c < G; ++c)
+      if (lane >= d) inc[c] += up[c];
+  }
+}
+template <int G>
+__device__ __forceinline__ void chunk_scans_down(double (&sfx)[G]) {
+  const int lane = lane_id();
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    double dn[G];
+#pragma unroll
+    for (int c = 0; c < G; ++c) dn[c] = shfl_down_f64(sfx[c], d);
+#pragma unroll
+    for (int c = 0; c < G; ++c)
+      if (lane + d < 32) sfx[c] += dn[c];
+  }
+}
+
+// Transmittance of every sample of the ray: x = sigma*delta (:41), float64 prefix sums rounded per element like torch's
+// cumsum, shifted to a true exclusive scan (:44-52).  The running sum across chunks is carry_c = carry_{c-1} + (chunk
+// c-1's total), the same additions the chunk-walking kernel makes.
+template <int G>
+__device__ __forceinline__ void transmittance(const float (&x)[G], float (&trans)[G]) {
+  const int lane = lane_id();
+  double inc[G];
+#pragma unroll
+  for (int c = 0; c < G; ++c) inc[c] = (double)x[c];
+  chunk_scans_up<G>(inc);
+  double carry = 0.0;
+#pragma unroll
+  for (int c = 0; c < G; ++c) {
+    const double tot = shfl_f64(inc[c], 31);
+    const float csum = (float)(inc[c] + carry);  // torch cumsum output element (float32)
+    float excl = __shfl_up_sync(0xffffffffu, csum, 1);
+    if (lane == 0) excl = (float)carry;
+    trans[c] = expf(-excl);
+    carry += tot;
+  }
+}
+
+template <int G>
+__global__ void __launch_bounds__(kCompWarps * 32)
+    composite_fwd_reg_kernel(const float* __restrict__ sigma, const float* __restrict__ radiance,
+                             const float* __restrict__ delta, const float* __restrict__ tvals, int64_t n, int s,
+                             float* __restrict__ rgb_out, float* __restrict__ w_out, float* __restrict__ depth_out,
+                             float* __restrict__ opacity_out) {
+  __shared__ float stage_all[kCompWarps][96 * G];
+  const int warp = threadIdx.x >> 5, lane = lane_id();
+  float* stage = stage_all[warp];
+  const int64_t ray = (int64_t)blockIdx.x * kCompWarps + warp;
+  if (ray >= n) return;
+  const float* sg_row = sigma + ray * s;
+  const float* dl_row = delta + ray * s;
+  const float* rad_row = radiance + ray * s * 3;
+  float x[G], tv[G];
+  {
+    float sg[G], dl[G], rad[3 * G];
+#pragma unroll
+    for (int c = 0; c < G; ++c) {
+      const int i = 32 * c + lane;
+      const bool ok = i < s;
+      sg[c] = ok ? __ldg(sg_row + i) : 0.f;
+      dl[c] = ok ? __ldg(dl_row + i) : 0.f;
+      tv[c] = (depth_out && ok) ? __ldg(tvals + ray * s + i) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 3 * G; ++k) {
+      const int e = 32 * k + lane;
+      rad[k] = e < 3 * s ? __ldg(rad_row + e) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 3 * G; ++k) stage[32 * k + lane] = rad[k];
+#pragma unroll
+    for (int c = 0; c < G; ++c) x[c] = __fmul_rn(sg[c], dl[c]);  // :41
+  }
+  __syncwarp();
+  float trans[G];
+  transmittance<G>(x, trans);
+  float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_d = 0.f, acc_o = 0.f;
+#pragma unroll
+  for (int c = 0; c < G; ++c) {
+    const int i = 32 * c + lane;
+    const bool ok = i < s;
+    const float alpha = __fsub_rn(1.0f, expf(-x[c]));       // :55
+    const float w = ok ? __fmul_rn(trans[c], alpha) : 0.f;  // :58
+    if (ok && w_out) w_out[ray * s + i] = w;
+    acc_r = fmaf(w, stage[3 * i], acc_r);
+    acc_g = fmaf(w, stage[3 * i + 1], acc_g);
+    acc_b = fmaf(w, stage[3 * i + 2], acc_b);
+    if (depth_out) acc_d = fmaf(w, tv[c], acc_d);
+    acc_o += w;
+  }
+  acc_r = warp_sum(acc_r), acc_g = warp_sum(acc_g), acc_b = warp_sum(acc_b);
+  if (depth_out) acc_d = warp_sum(acc_d);
+  if (opacity_out) acc_o = warp_sum(acc_o);
+  if (lane == 0) {
+    rgb_out[3 * ray + 0] = acc_r;
+    rgb_out[3 * ray + 1] = acc_g;
+    rgb_out[3 * ray + 2] = acc_b;
+    if (depth_out) depth_out[ray] = acc_d;
+    if (opacity_out) opacity_out[ray] = acc_o;
+  }
+}
+
+template <int G>
+__global__ void __launch_bounds__(kCompWarps * 32)
+    composite_bwd_reg_kernel(const float* __restrict__ sigma, const float* __restrict__ radiance,
+                             const float* __restrict__ delta, const float* __restrict__ g_rgb,
+                             const float* __restrict__ g_w_ext, int64_t n, int s, float* __restrict__ g_sigma,
+                             float* __restrict__ g_radiance) {
+  __shared__ float stage_all[kCompWarps][96 * G];
+  const int warp = threadIdx.x >> 5, lane = lane_id();
+  float* stage = stage_all[warp];
+  const int64_t ray = (int64_t)blockIdx.x * kCompWarps + warp;
+  if (ray >= n) return;
+  const float* sg_row = sigma + ray * s;
+  const float* dl_row = delta + ray * s;
+  const float* rad_row = radiance + ray * s * 3;
+  float x[G], dl[G], gw[G];
+  {
+    float sg[G], rad[3 * G];
+#pragma unroll
+    for (int c = 0; c < G; ++c) {
+      const int i = 32 * c + lane;
+      const bool ok = i < s;
+      sg[c] = ok ? __ldg(sg_row + i) : 0.f;
+      dl[c] = ok ? __ldg(dl_row + i) : 0.f;
+      gw[c] = (g_w_ext && ok) ? __ldg(g_w_ext + ray * s + i) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 3 * G; ++k) {
+      const int e = 32 * k + lane;
+      rad[k] = e < 3 * s ? __ldg(rad_row + e) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 3 * G; ++k) stage[32 * k + lane] = rad[k];
+#pragma unroll
+    for (int c = 0; c < G; ++c) x[c] = __fmul_rn(sg[c], dl[c]);
+  }
+  const float gr = __ldg(g_rgb + 3 * ray), gg = __ldg(g_rgb + 3 * ray + 1), gb = __ldg(g_rgb + 3 * ray + 2);
+  __syncwarp();
+  float trans[G];
+  transmittance<G>(x, trans);
+  // per sample: w, T_{i+1} = T_i e^{-x_i}, g_w = g_rgb . c (+ external)
+  float w[G], tnext[G];
+  double sfx[G];
+#pragma unroll
+  for (int c = 0; c < G; ++c) {
+    const int i = 32 * c + lane;
+    const bool ok = i < s;
+    const float ex = expf(-x[c]);
+    w[c] = ok ? __fmul_rn(trans[c], __fsub_rn(1.0f, ex)) : 0.f;
+    tnext[c] = trans[c] * ex;
+    const float r = stage[3 * i], g = stage[3 * i + 1], b = stage[3 * i + 2];
+    gw[c] += gr * r + gg * g + gb * b;
+    sfx[c] = ok ? (double)gw[c] * (double)w[c] : 0.0;
+  }
+  __syncwarp();  // every lane has read its radiance: the staging rows now collect g_c = w * g_rgb
+  // exclusive suffix scans of gw*w (float64): inside the chunks, then the carry from the far end
+  chunk_scans_down<G>(sfx);
+  double suffix = 0.0;  // sum_{k > last element of this chunk} g_w_k w_k
+#pragma unroll
+  for (int c = G - 1; c >= 0; --c) {
+    const int i = 32 * c + lane;
+    const bool ok = i < s;
+    double sfx_excl = shfl_down_f64(sfx[c], 1);
+    if (lane == 31) sfx_excl = 0.0;
+    sfx_excl += suffix;
+    if (ok) {
+      const float gx = (float)((double)gw[c] * (double)tnext[c] - sfx_excl);
+      g_sigma[ray * s + i] = dl[c] * gx;
+    }
+    stage[3 * i] = w[c] * gr;
+    stage[3 * i + 1] = w[c] * gg;
+    stage[3 * i + 2] = w[c] * gb;
+    suffix += shfl_f64(sfx[c], 0);
+  }
+  __syncwarp();
+  float* dst = g_radiance + ray * s * 3;
+#pragma unroll
+  for (int k = 0; k < 3 * G; ++k) {
+    const int e = 32 * k + lane;
+    if (e < 3 * s) dst[e] = stage[e];
+  }
+}
+
+template <int G>
+static void launch_composite_fwd_reg(const float* sigma, const float* radiance, const float* delta, const float* t,
+                                     int64_t n, int s, float* rgb, float* w, float* depth, float* opacity,
+                                     cudaStream_t stream) {
+  composite_fwd_reg_kernel<G><<<(unsigned)ceil_div64(n, kCompWarps), kCompWarps * 32, 0, stream>>>(
+      sigma, radiance, delta, t, n, s, rgb, w, depth, opacity);
+}
+template <int G>
+static void launch_composite_bwd_reg(const float* sigma, const float* radiance, const float* delta, const float* g_rgb,
+                                     const float* g_w, int64_t n, int s, float* g_sigma, float* g_radiance,
+                                     cudaStream_t stream) {
+  composite_bwd_reg_kernel<G><<<(unsigned)ceil_div64(n, kCompWarps), kCompWarps * 32, 0, stream>>>(
+      sigma, radiance, delta, g_rgb, g_w, n, s, g_sigma, g_radiance);
+}
+
 }  // namespace nerf
 
 using namespace nerf;
@@ -278,8 +496,14 @@ int nerf_composite_fwd(const float* sigma_dev, const float* radiance_dev, const 
   NERF_CHECK_ARG(sigma_dev && radiance_dev && delta_dev && rgb_dev, "nerf_composite_fwd: null pointer");
   NERF_CHECK_ARG(depth_dev == nullptr || t_dev != nullptr, "nerf_composite_fwd: depth needs t");
   if (n == 0) return NERF_OK;
-  composite_fwd_kernel<<<(unsigned)ceil_div64(n, kCompWarps), kCompWarps * 32, 0, as_stream(stream)>>>(
-      sigma_dev, radiance_dev, delta_dev, t_dev, n, s, rgb_dev, w_dev, depth_dev, opacity_dev);
+  cudaStream_t cs = as_stream(stream);
+  if (s <= 64) launch_composite_fwd_reg<2>(sigma_dev, radiance_dev, delta_dev, t_dev, n, s, rgb_dev, w_dev, depth_dev, opacity_dev, cs);
+  else if (s <= 128) launch_composite_fwd_reg<4>(sigma_dev, radiance_dev, delta_dev, t_dev, n, s, rgb_dev, w_dev, depth_dev, opacity_dev, cs);
+  else if (s <= 192) launch_composite_fwd_reg<6>(sigma_dev, radiance_dev, delta_dev, t_dev, n, s, rgb_dev, w_dev, depth_dev, opacity_dev, cs);
+  else if (s <= 256) launch_composite_fwd_reg<8>(sigma_dev, radiance_dev, delta_dev, t_dev, n, s, rgb_dev, w_dev, depth_dev, opacity_dev, cs);
+  else
+    composite_fwd_kernel<<<(unsigned)ceil_div64(n, kCompWarps), kCompWarps * 32, 0, cs>>>(
+        sigma_dev, radiance_dev, delta_dev, t_dev, n, s, rgb_dev, w_dev, depth_dev, opacity_dev);
   NERF_LAUNCH_CHECK();
   return NERF_OK;
 }
@@ -292,8 +516,14 @@ int nerf_composite_bwd(const float* sigma_dev, const float* radiance_dev, const 
   NERF_CHECK_ARG(sigma_dev && radiance_dev && delta_dev && g_rgb_dev && g_sigma_dev && g_radiance_dev,
                  "nerf_composite_bwd: null pointer");
   if (n == 0) return NERF_OK;
-  composite_bwd_kernel<<<(unsigned)ceil_div64(n, kCompWarps), kCompWarps * 32, 0, as_stream(stream)>>>(
-      sigma_dev, radiance_dev, delta_dev, g_rgb_dev, g_w_dev, n, s, g_sigma_dev, g_radiance_dev);
+  cudaStream_t cs = as_stream(stream);
+  if (s <= 64) launch_composite_bwd_reg<2>(sigma_dev, radiance_dev, delta_dev, g_rgb_dev, g_w_dev, n, s, g_sigma_dev, g_radiance_dev, cs);
+  else if (s <= 128) launch_composite_bwd_reg<4>(sigma_dev, radiance_dev, delta_dev, g_rgb_dev, g_w_dev, n, s, g_sigma_dev, g_radiance_dev, cs);
+  else if (s <= 192) launch_composite_bwd_reg<6>(sigma_dev, radiance_dev, delta_dev, g_rgb_dev, g_w_dev, n, s, g_sigma_dev, g_radiance_dev, cs);
+  else if (s <= 256) launch_composite_bwd_reg<8>(sigma_dev, radiance_dev, delta_dev, g_rgb_dev, g_w_dev, n, s, g_sigma_dev, g_radiance_dev, cs);
+  else
+    composite_bwd_kernel<<<(unsigned)ceil_div64(n, kCompWarps), kCompWarps * 32, 0, cs>>>(
+        sigma_dev, radiance_dev, delta_dev, g_rgb_dev, g_w_dev, n, s, g_sigma_dev, g_radiance_dev);
   NERF_LAUNCH_CHECK();
   return NERF_OK;
 }

@@ -19,12 +19,10 @@ namespace nerf {
 // ------------------------------------------------------------------------------------------------
 // K1
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) raygen_kernel(const int64_t* __restrict__ coords,
-                                                      const int64_t* __restrict__ pix, int64_t first_pixel,
-                                                      int64_t n, nerf_camera_t cam, float* __restrict__ ray_o,
-                                                      float* __restrict__ ray_d) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+constexpr int kRaysPerThread = 4;  // 4 rays = 12 floats = three 16-byte stores per output
+
+__device__ __forceinline__ void one_ray(const int64_t* __restrict__ coords, const int64_t* __restrict__ pix,
+                                        int64_t first_pixel, int64_t i, const nerf_camera_t& cam, float* o, float* d) {
   float u, v;
   if (coords != nullptr) {
     u = (float)coords[2 * i];
@@ -40,7 +38,6 @@ __global__ void __launch_bounds__(256) raygen_kernel(const int64_t* __restrict__
   float x = __fdiv_rn(__fsub_rn(u, cam.cx), cam.fx);
   float y = __fdiv_rn(__fsub_rn(v, cam.cy), cam.fy);
   // sampler_base.py:164  d = [x, y, -1] @ R^T
-  float d[3], o[3];
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     float acc = __fmul_rn(x, cam.rot[3 * j + 0]);
@@ -63,10 +60,35 @@ __global__ void __launch_bounds__(256) raygen_kernel(const int64_t* __restrict__
     o[0] = no0, o[1] = no1, o[2] = no2;
     d[0] = nd0, d[1] = nd1, d[2] = nd2;
   }
+}
+
+__global__ void __launch_bounds__(256) raygen_kernel(const int64_t* __restrict__ coords,
+                                                      const int64_t* __restrict__ pix, int64_t first_pixel,
+                                                      int64_t n, nerf_camera_t cam, float* __restrict__ ray_o,
+                                                      float* __restrict__ ray_d, int vec_ok) {
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * kRaysPerThread;
+  if (i0 >= n) return;
+  if (vec_ok && i0 + kRaysPerThread <= n) {
+    float o[3 * kRaysPerThread], d[3 * kRaysPerThread];
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    ray_o[3 * i + j] = o[j];
-    ray_d[3 * i + j] = d[j];
+    for (int r = 0; r < kRaysPerThread; ++r) one_ray(coords, pix, first_pixel, i0 + r, cam, o + 3 * r, d + 3 * r);
+    float4* dst_o = reinterpret_cast<float4*>(ray_o + 3 * i0);  // 48-byte slabs of a 16-byte aligned array
+    float4* dst_d = reinterpret_cast<float4*>(ray_d + 3 * i0);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      dst_o[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+      dst_d[k] = make_float4(d[4 * k], d[4 * k + 1], d[4 * k + 2], d[4 * k + 3]);
+    }
+  } else {
+    for (int64_t i = i0; i < min(i0 + kRaysPerThread, n); ++i) {
+      float o[3], d[3];
+      one_ray(coords, pix, first_pixel, i, cam, o, d);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        ray_o[3 * i + j] = o[j];
+        ray_d[3 * i + j] = d[j];
+      }
+    }
   }
 }
 
@@ -159,6 +181,30 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
   emit_samples(ts, s, ray, ray_o, ray_d, t_out, pts, dirs, delta, stage);
 }
 
+// K2 without the (N,S,3) outputs (the fused engine's form): nothing couples the samples of a ray except the forward
+// difference, so this is an elementwise stream -- one thread per four consecutive samples, 16-byte loads and stores;
+// the first sample of the next quad is recomputed from one extra scalar load (same sector, no extra HBM traffic).
+__global__ void __launch_bounds__(256)
+    sample_coarse_flat_kernel(int64_t quads, int s, BinSpec bins, const float* __restrict__ u,
+                              float* __restrict__ t_out, float* __restrict__ delta) {
+  const int64_t q4 = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (q4 >= quads) return;
+  const int s4 = s >> 2;
+  const int i = 4 * (quads <= 0x7fffffff ? (int)((unsigned)q4 % (unsigned)s4) : (int)(q4 % s4));
+  const int64_t q = 4 * q4;
+  const float4 uv = __ldg(reinterpret_cast<const float4*>(u + q));
+  float t[5];
+  t[0] = __fadd_rn(bin_at(bins, i), __fmul_rn(bins.step, uv.x));
+  t[1] = __fadd_rn(bin_at(bins, i + 1), __fmul_rn(bins.step, uv.y));
+  t[2] = __fadd_rn(bin_at(bins, i + 2), __fmul_rn(bins.step, uv.z));
+  t[3] = __fadd_rn(bin_at(bins, i + 3), __fmul_rn(bins.step, uv.w));
+  t[4] = (i + 4 < s) ? __fadd_rn(bin_at(bins, i + 4), __fmul_rn(bins.step, __ldg(u + q + 4))) : 1e8f;  // :112-119
+  if (t_out) *reinterpret_cast<float4*>(t_out + q) = make_float4(t[0], t[1], t[2], t[3]);
+  if (delta)
+    *reinterpret_cast<float4*>(delta + q) =
+        make_float4(__fsub_rn(t[1], t[0]), __fsub_rn(t[2], t[1]), __fsub_rn(t[3], t[2]), __fsub_rn(t[4], t[3]));
+}
+
 // ------------------------------------------------------------------------------------------------
 // K3
 // ------------------------------------------------------------------------------------------------
@@ -198,10 +244,37 @@ __device__ __forceinline__ void build_cdf(float* __restrict__ weights_row, int s
   __syncwarp();
   float z = torch_cpu_row_sum(ws, sc);  // utils.py:32
   __syncwarp();
-  for (int i = lane; i < sc; i += 32) ws[i] = __fdiv_rn(ws[i], z);  // utils.py:33
+  bool exact = true;
+  for (int i = lane; i < sc; i += 32) {
+    const float pdf = __fdiv_rn(ws[i], z);  // utils.py:33
+    ws[i] = pdf;
+    exact = exact && (pdf >= 0x1p-28f) && (pdf <= 1.0f);
+  }
   __syncwarp();
-  if (lane == 0) {
-    // utils.py:36-40: cumsum with a float64 running sum rounded per element, shifted to exclusive
+  // utils.py:36-40: cumsum with a float64 running sum rounded per element, shifted to exclusive.
+  // When every pdf value is in [2^-28, 1] (always the case for compositing weights: w + 1e-5 over a sum <= ~1) each is
+  // a multiple of 2^-51; all pdf > 0 means all weights share the sign of their float32 sum z, whose relative error
+  // is at most ~sc * 2^-24, so every partial sum stays below 2 and fits 52 significant bits: ALL float64 partial sums
+  // are exact whatever the order, and a warp scan returns exactly the sequential running sum.  Anything else (huge
+  // dynamic range, mixed signs, NaN) takes the sequential loop.
+  if (__all_sync(0xffffffffu, exact) && sc <= 1024) {
+    double carry = 0.0;
+    if (lane == 0) cdf[0] = 0.f;
+    for (int base = 0; base < sc; base += 32) {
+      const int j = base + lane;
+      double inc = j < sc ? (double)ws[j] : 0.0;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const double up = __hiloint2double(__shfl_up_sync(0xffffffffu, __double2hiint(inc), d),
+                                           __shfl_up_sync(0xffffffffu, __double2loint(inc), d));
+        if (lane >= d) inc += up;
+      }
+      inc += carry;
+      if (j + 1 < sc) cdf[j + 1] = (float)inc;
+      carry = __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(inc), 31),
+                               __shfl_sync(0xffffffffu, __double2loint(inc), 31));
+    }
+  } else if (lane == 0) {
     double run = 0.0;
     cdf[0] = 0.f;
     for (int j = 0; j + 1 < sc; ++j) {
@@ -291,6 +364,147 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
   emit_samples(ts, s, ray, ray_o, ray_d, t_out, pts, dirs, delta, stage);
 }
 
+// ------------------------------------------------------------------------------------------------
+// K3 fast path for the reference's default counts (64 coarse + 128 fine): the 256-wide bitonic network in shared
+// memory is what the general kernel spends its time on (36 stages, ~1700 warp instructions per ray).  Here the two sets
+// are sorted separately IN REGISTERS (element e of a set lives in slot e / 32 of lane e % 32; stages with a partner
+// distance below 32 are one shuffle + min/max, the others stay inside the lane), then merged by rank: every element's
+// final position is its own index plus a binary-search count in the other set.  Same multiset, same order, so the
+// output is bit-identical to the full sort.
+// ------------------------------------------------------------------------------------------------
+template <int NSLOT>
+__device__ __forceinline__ void warp_bitonic_sort_regs(float (&v)[NSLOT]) {
+  const int lane = lane_id();
+#pragma unroll
+  for (int k = 2; k <= 32 * NSLOT; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const int jr = j >> 5;
+#pragma unroll
+        for (int r = 0; r < NSLOT; ++r) {
+          if ((r & jr) == 0) {
+            const bool up = (((r << 5) & k) == 0);  // k >= 64 here: the direction depends on the slot only
+            const float lo = fminf(v[r], v[r | jr]), hi = fmaxf(v[r], v[r | jr]);
+            v[r] = up ? lo : hi;
+            v[r | jr] = up ? hi : lo;
+          }
+        }
+      } else {
+        const bool lower = (lane & j) == 0;
+#pragma unroll
+        for (int r = 0; r < NSLOT; ++r) {
+          const float other = __shfl_xor_sync(0xffffffffu, v[r], j);
+          const bool up = ((((r << 5) | lane) & k) == 0);
+          v[r] = (up == lower) ? fminf(v[r], other) : fmaxf(v[r], other);
+        }
+      }
+    }
+  }
+}
+
+// Branch-free binary searches over power-of-two arrays, R independent keys per lane advanced in lock step (the loads
+// of the R searches overlap; no lane-dependent trip counts).
+// count[r] = number of elements of the ascending array a[0..N) that are < x[r] (strict) or <= x[r]
+template <int N, int R, bool kOrEqual>
+__device__ __forceinline__ void count_below(const float* a, const float (&x)[R], int (&count)[R]) {
+#pragma unroll
+  for (int r = 0; r < R; ++r) count[r] = 0;
+#pragma unroll
+  for (int step = N / 2; step > 0; step >>= 1) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float v = a[count[r] + step - 1];
+      count[r] += (kOrEqual ? (v <= x[r]) : (v < x[r])) ? step : 0;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {  // the loop stops at min(count, N-1): one more probe tells N-1 from N
+    const float v = a[count[r]];
+    count[r] += (kOrEqual ? (v <= x[r]) : (v < x[r])) ? 1 : 0;
+  }
+}
+
+constexpr int kFastSc = 64, kFastSf = 128;
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+    sample_fine_64_128_kernel(const float* __restrict__ ray_o, const float* __restrict__ ray_d, int64_t n, BinSpec bins,
+                              float* __restrict__ weights, const float* __restrict__ u0, const float* __restrict__ u1,
+                              const float* __restrict__ u2, int64_t* __restrict__ idx_out, float* __restrict__ t_out,
+                              float* __restrict__ pts, float* __restrict__ dirs, float* __restrict__ delta) {
+  constexpr int sc = kFastSc, sf = kFastSf, s = sc + sf;
+  // per warp: merged t (192) | sorted coarse (64) | sorted fine (128) | normalised weights (64) | cdf (64) | staging (96)
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = lane_id();
+  float* ts = smem + warp * (s + sc + sf + 2 * sc + 96);
+  float* sa = ts + s;
+  float* sb = sa + sc;
+  float* ws = sb + sf;
+  float* cdf = ws + sc;
+  float* stage = cdf + sc;
+  const int64_t ray = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  if (ray >= n) return;
+  // every global load of the ray is issued before the CDF is built
+  float uc[2], ua[4], ub[4];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) uc[r] = __ldg(u0 + ray * sc + 32 * r + lane);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    ua[r] = __ldg(u1 + ray * sf + 32 * r + lane);
+    ub[r] = __ldg(u2 + ray * sf + 32 * r + lane);
+  }
+  build_cdf(weights + ray * sc, sc, ws, cdf);
+  float tc[2], tf[4];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)  // stratified_sampler.py:77: a fresh stratified draw, not the coarse pass's samples
+    tc[r] = __fadd_rn(bin_at(bins, 32 * r + lane), __fmul_rn(bins.step, uc[r]));
+  {
+    // idx = #(cdf_j <= u) - 1 (utils.py:47-54); cdf[0] = 0 <= u for every u in [0,1), so count over cdf[1..63] instead
+    int idx[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) idx[r] = 0;
+#pragma unroll
+    for (int step = sc / 2; step > 0; step >>= 1) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) idx[r] += (cdf[idx[r] + step] <= ua[r]) ? step : 0;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (!(0.f <= ua[r])) idx[r] = -1;  // out-of-contract draws (negative, NaN) behave like the general kernel
+      if (idx_out) idx_out[ray * sf + 32 * r + lane] = idx[r];
+      tf[r] = __fadd_rn(bin_at(bins, idx[r]), __fmul_rn(bins.step, ub[r]));  // utils.py:55-56
+    }
+  }
+  // the stratified draw is ascending by construction whenever the bins are exact in float32 (the shipped scene bounds);
+  // sort it only if a neighbour pair is out of order
+  {
+    const float nxt0 = __shfl_down_sync(0xffffffffu, tc[0], 1), first1 = __shfl_sync(0xffffffffu, tc[1], 0);
+    const float nxt1 = __shfl_down_sync(0xffffffffu, tc[1], 1);
+    const bool bad = (tc[0] > (lane == 31 ? first1 : nxt0)) || (lane < 31 && tc[1] > nxt1);
+    if (__any_sync(0xffffffffu, bad)) warp_bitonic_sort_regs<2>(tc);
+  }
+  warp_bitonic_sort_regs<4>(tf);
+#pragma unroll
+  for (int r = 0; r < 2; ++r) sa[32 * r + lane] = tc[r];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) sb[32 * r + lane] = tf[r];
+  __syncwarp();
+  // merge (stratified_sampler.py:87-90 sorts the concatenation): ties put the coarse element first
+  int below_c[2], below_f[4];
+  count_below<sf, 2, false>(sb, tc, below_c);
+  count_below<sc, 4, true>(sa, tf, below_f);
+#pragma unroll
+  for (int r = 0; r < 2; ++r) ts[32 * r + lane + below_c[r]] = tc[r];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) ts[32 * r + lane + below_f[r]] = tf[r];
+  __syncwarp();
+  emit_samples(ts, s, ray, ray_o, ray_d, t_out, pts, dirs, delta, stage);
+}
+
+static int aligned16(const void* a, const void* b) {
+  return (((uintptr_t)a | (uintptr_t)b) & 15) == 0;
+}
+
 static int next_pow2(int v) {
   int p = 1;
   while (p < v) p <<= 1;
@@ -308,8 +522,9 @@ int nerf_generate_rays(const int64_t* coords_dev, int64_t n, const nerf_camera_t
   NERF_CHECK_ARG(n >= 0, "nerf_generate_rays: negative ray count");
   if (n == 0) return NERF_OK;
   NERF_CHECK_ARG(cam && coords_dev && ray_o_dev && ray_d_dev, "nerf_generate_rays: null pointer");
-  raygen_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, as_stream(stream)>>>(coords_dev, nullptr, 0, n, *cam,
-                                                                             ray_o_dev, ray_d_dev);
+  raygen_kernel<<<(unsigned)ceil_div64(n, 256 * kRaysPerThread), 256, 0, as_stream(stream)>>>(coords_dev, nullptr, 0, n, *cam,
+                                                                             ray_o_dev, ray_d_dev,
+                                                                             aligned16(ray_o_dev, ray_d_dev));
   NERF_LAUNCH_CHECK();
   return NERF_OK;
 }
@@ -321,8 +536,9 @@ int nerf_generate_rays_from_pixels(const int64_t* pixel_idx_dev, int64_t first_p
   if (n == 0) return NERF_OK;
   NERF_CHECK_ARG(cam && ray_o_dev && ray_d_dev, "nerf_generate_rays_from_pixels: null pointer");
   NERF_CHECK_ARG(cam->img_w > 0 && cam->img_h > 0, "nerf_generate_rays_from_pixels: bad image size");
-  raygen_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, as_stream(stream)>>>(nullptr, pixel_idx_dev, first_pixel, n,
-                                                                             *cam, ray_o_dev, ray_d_dev);
+  raygen_kernel<<<(unsigned)ceil_div64(n, 256 * kRaysPerThread), 256, 0, as_stream(stream)>>>(nullptr, pixel_idx_dev, first_pixel, n,
+                                                                             *cam, ray_o_dev, ray_d_dev,
+                                                                             aligned16(ray_o_dev, ray_d_dev));
   NERF_LAUNCH_CHECK();
   return NERF_OK;
 }
@@ -350,6 +566,14 @@ int nerf_sample_coarse(const float* ray_o_dev, const float* ray_d_dev, int64_t n
   NERF_CHECK_ARG(n >= 0, "nerf_sample_coarse: negative ray count");
   if (n == 0) return NERF_OK;  // empty ray set: nothing to do (zero-size tensors have null data pointers)
   NERF_CHECK_ARG(ray_o_dev && ray_d_dev && u_dev, "nerf_sample_coarse: null pointer");
+  if (!pts_dev && !dirs_dev && num_samples % 4 == 0 && ((uintptr_t)u_dev & 15) == 0 &&
+      aligned16(t_dev, delta_dev)) {
+    const int64_t quads = n * (num_samples / 4);
+    sample_coarse_flat_kernel<<<(unsigned)ceil_div64(quads, 256), 256, 0, as_stream(stream)>>>(
+        quads, num_samples, make_bin_spec(t_near, t_far, num_samples), u_dev, t_dev, delta_dev);
+    NERF_LAUNCH_CHECK();
+    return NERF_OK;
+  }
   size_t smem = sizeof(float) * kWarpsPerBlock * (num_samples + 96);
   sample_coarse_kernel<<<(unsigned)ceil_div64(n, kWarpsPerBlock), kWarpsPerBlock * 32, smem, as_stream(stream)>>>(
       ray_o_dev, ray_d_dev, n, num_samples, make_bin_spec(t_near, t_far, num_samples), u_dev, t_dev, pts_dev, dirs_dev,
@@ -383,6 +607,14 @@ int nerf_sample_fine(const float* ray_o_dev, const float* ray_d_dev, int64_t n, 
   if (n == 0) return NERF_OK;
   NERF_CHECK_ARG(ray_o_dev && ray_d_dev && weights_dev && u0_dev && u1_dev && u2_dev,
                  "nerf_sample_fine: null pointer");
+  if (num_coarse == kFastSc && num_fine == kFastSf) {
+    const size_t smem_fast = sizeof(float) * kWarpsPerBlock * ((kFastSc + kFastSf) * 2 + 2 * kFastSc + 96);
+    sample_fine_64_128_kernel<<<(unsigned)ceil_div64(n, kWarpsPerBlock), kWarpsPerBlock * 32, smem_fast, as_stream(stream)>>>(
+        ray_o_dev, ray_d_dev, n, make_bin_spec(t_near, t_far, num_coarse), weights_dev, u0_dev, u1_dev, u2_dev, idx_dev, t_dev,
+        pts_dev, dirs_dev, delta_dev);
+    NERF_LAUNCH_CHECK();
+    return NERF_OK;
+  }
   const int p2 = next_pow2(num_coarse + num_fine);
   size_t smem = sizeof(float) * kWarpsPerBlock * (p2 + 2 * num_coarse + 96);
   if (smem > 48 * 1024) {
