@@ -68,6 +68,15 @@ int nerf_generate_rays_from_pixels(const int64_t* pixel_idx_dev, int64_t first_p
                                    const nerf_camera_t* cam, float* ray_o_dev, float* ray_d_dev,
                                    nerf_stream_t stream);
 
+/* The same with the camera in DEVICE memory, for callers that capture the training iteration (runners/train.py:130-218)
+ * into a CUDA graph: the reference builds a new PerspectiveCamera per iteration (train.py:136-145), so the camera must
+ * not be baked into the captured launch parameters.  nerf_upload_camera writes *cam to cam_dev on the stream (the
+ * struct travels in the launch parameters; cam may be reused by the host as soon as the call returns). */
+int nerf_upload_camera(nerf_camera_t* cam_dev, const nerf_camera_t* cam, nerf_stream_t stream);
+int nerf_generate_rays_from_pixels_devcam(const int64_t* pixel_idx_dev, int64_t first_pixel, int64_t n,
+                                          const nerf_camera_t* cam_dev, float* ray_o_dev, float* ray_d_dev,
+                                          nerf_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K2 / K3 sampling along rays
  *   replaces StratifiedSampler.sample_along_rays (src/renderer/ray_samplers/stratified_sampler.py:17-128)

@@ -265,3 +265,46 @@ def test_config_c5_llff_ndc_train_step_fp32_vs_oracle(tn, near):
             cos = float((got * r).sum() / (np.linalg.norm(got) * np.linalg.norm(r) + 1e-300))
             assert cos > 0.9995, (tag, k, cos)
             assert np.abs(got - r).max() <= 0.08 * np.abs(r).max() + 1e-12, (tag, k)
+
+
+def test_engine_graph_replay_matches_eager(tn):
+    """The CUDA-graph-captured iteration (train_pixels_graph) against the eager one: a new camera, new pixels and new
+    targets every iteration must reach the replayed kernels (rays bit-identical, losses and gradients equal up to the
+    order of the fp32 atomics), with the same torch seed giving the same uniform draws."""
+    from torch_nerf_b200.engine import HotPathEngine
+
+    n, h = 1024, 200
+    focal = orc.blender_focal(h)
+    gen = torch.Generator().manual_seed(3)
+    cams, pixs, tgts = [], [], []
+    for i in range(4):
+        c2w = torch.from_numpy(orc.pose_spherical(70.0 * i - 100.0, -30.0 + 5 * i, 4.0))
+        cams.append(tn.PerspectiveCamera({"f_x": focal, "f_y": focal, "img_width": h, "img_height": h}, c2w, 2.0, 6.0))
+        pixs.append(torch.randperm(h * h, generator=gen)[:n])
+        tgts.append(torch.rand((n, 3), generator=gen))
+    out = {}
+    for mode in ("eager", "graph"):
+        coarse, fine = nets(tn, 71, 72, "bf16")
+        eng = HotPathEngine(coarse, fine, 64, 128, precision="bf16")
+        flat = eng.enable_flat_params()
+        torch.manual_seed(21)
+        rec = []
+        for i in range(4):
+            if mode == "eager":
+                losses = eng.train_pixels(cams[i], pixs[i].cuda(), tgts[i].cuda(), False)
+            else:  # pinned host inputs on odd iterations, device inputs on even ones
+                src = (pixs[i].pin_memory(), tgts[i].pin_memory()) if i % 2 else (pixs[i].cuda(), tgts[i].cuda())
+                losses = eng.train_pixels_graph(cams[i], src[0], src[1], False)
+            rec.append((losses.clone(), flat.grad.clone(), eng._get("ray_o", (n, 3)).clone(), eng._get("ray_d", (n, 3)).clone(),
+                        eng.last["fine"]["rgb"].clone()))
+        out[mode] = rec
+        if mode == "graph":
+            assert len(eng._graphs) == 1 and next(iter(eng._graphs.values())).launches > 10
+    for i in range(4):
+        le, ge, oe, de, re = out["eager"][i]
+        lg, gg, og, dg, rg = out["graph"][i]
+        assert torch.equal(oe, og) and torch.equal(de, dg), f"iteration {i}: the replay used a stale camera or pixel batch"
+        torch.testing.assert_close(lg, le, rtol=2e-3, atol=1e-6)
+        torch.testing.assert_close(rg, re, rtol=0, atol=2e-2)
+        cos = torch.nn.functional.cosine_similarity(gg, ge, dim=0)
+        assert float(cos) > 0.995, (i, float(cos))

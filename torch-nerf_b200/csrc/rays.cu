@@ -28,9 +28,15 @@ __device__ __forceinline__ void one_ray(const int64_t* __restrict__ coords, cons
     u = (float)coords[2 * i];
     v = (float)coords[2 * i + 1];
   } else {
-    int64_t p = pix != nullptr ? pix[i] : first_pixel + i;
-    int64_t row = p / cam.img_w;
-    int64_t col = p - row * cam.img_w;
+    const int64_t p = pix != nullptr ? pix[i] : first_pixel + i;
+    int64_t row, col;
+    if ((uint64_t)p <= 0xffffffffu) {  // 32-bit division: a fraction of the instructions of the 64-bit one
+      row = (uint32_t)p / (uint32_t)cam.img_w;
+      col = (uint32_t)p - (uint32_t)row * (uint32_t)cam.img_w;
+    } else {
+      row = p / cam.img_w;
+      col = p - row * cam.img_w;
+    }
     u = (float)col;                        // volume_renderer.py:179-188: (u = col, v = H-1-row)
     v = (float)((int64_t)cam.img_h - 1 - row);
   }
@@ -62,10 +68,15 @@ __device__ __forceinline__ void one_ray(const int64_t* __restrict__ coords, cons
   }
 }
 
+// `cam_dev` != null: the camera is read from device memory (a captured CUDA graph replays with whatever camera
+// nerf_upload_camera put there); otherwise it travels by value in the launch parameters.
 __global__ void __launch_bounds__(256) raygen_kernel(const int64_t* __restrict__ coords,
                                                       const int64_t* __restrict__ pix, int64_t first_pixel,
-                                                      int64_t n, nerf_camera_t cam, float* __restrict__ ray_o,
-                                                      float* __restrict__ ray_d, int vec_ok) {
+                                                      int64_t n, nerf_camera_t cam_arg,
+                                                      const nerf_camera_t* __restrict__ cam_dev,
+                                                      float* __restrict__ ray_o, float* __restrict__ ray_d, int vec_ok) {
+  nerf_camera_t cam = cam_arg;
+  if (cam_dev != nullptr) cam = *cam_dev;
   const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * kRaysPerThread;
   if (i0 >= n) return;
   if (vec_ok && i0 + kRaysPerThread <= n) {
@@ -90,6 +101,10 @@ __global__ void __launch_bounds__(256) raygen_kernel(const int64_t* __restrict__
       }
     }
   }
+}
+
+__global__ void store_camera_kernel(nerf_camera_t* dst, nerf_camera_t cam) {
+  if (threadIdx.x == 0) *dst = cam;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -396,7 +411,9 @@ __device__ __forceinline__ void warp_bitonic_sort_regs(float (&v)[NSLOT]) {
         for (int r = 0; r < NSLOT; ++r) {
           const float other = __shfl_xor_sync(0xffffffffu, v[r], j);
           const bool up = ((((r << 5) | lane) & k) == 0);
-          v[r] = (up == lower) ? fminf(v[r], other) : fmaxf(v[r], other);
+          // keep the minimum iff up == lower; one compare (xor-ed with the direction) + one select per exchange
+          const bool take = (v[r] > other) != (up != lower);
+          v[r] = take ? other : v[r];
         }
       }
     }
@@ -522,7 +539,7 @@ int nerf_generate_rays(const int64_t* coords_dev, int64_t n, const nerf_camera_t
   NERF_CHECK_ARG(n >= 0, "nerf_generate_rays: negative ray count");
   if (n == 0) return NERF_OK;
   NERF_CHECK_ARG(cam && coords_dev && ray_o_dev && ray_d_dev, "nerf_generate_rays: null pointer");
-  raygen_kernel<<<(unsigned)ceil_div64(n, 256 * kRaysPerThread), 256, 0, as_stream(stream)>>>(coords_dev, nullptr, 0, n, *cam,
+  raygen_kernel<<<(unsigned)ceil_div64(n, 256 * kRaysPerThread), 256, 0, as_stream(stream)>>>(coords_dev, nullptr, 0, n, *cam, nullptr,
                                                                              ray_o_dev, ray_d_dev,
                                                                              aligned16(ray_o_dev, ray_d_dev));
   NERF_LAUNCH_CHECK();
@@ -537,8 +554,30 @@ int nerf_generate_rays_from_pixels(const int64_t* pixel_idx_dev, int64_t first_p
   NERF_CHECK_ARG(cam && ray_o_dev && ray_d_dev, "nerf_generate_rays_from_pixels: null pointer");
   NERF_CHECK_ARG(cam->img_w > 0 && cam->img_h > 0, "nerf_generate_rays_from_pixels: bad image size");
   raygen_kernel<<<(unsigned)ceil_div64(n, 256 * kRaysPerThread), 256, 0, as_stream(stream)>>>(nullptr, pixel_idx_dev, first_pixel, n,
-                                                                             *cam, ray_o_dev, ray_d_dev,
+                                                                             *cam, nullptr, ray_o_dev, ray_d_dev,
                                                                              aligned16(ray_o_dev, ray_d_dev));
+  NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
+
+int nerf_upload_camera(nerf_camera_t* cam_dev, const nerf_camera_t* cam, nerf_stream_t stream) {
+  NERF_CHECK_ARG(cam_dev && cam, "nerf_upload_camera: null pointer");
+  // the struct rides in the launch parameters (copied at launch time): no pinned staging buffer whose lifetime the
+  // caller would have to manage, and the write is ordered on the stream like any kernel
+  store_camera_kernel<<<1, 32, 0, as_stream(stream)>>>(cam_dev, *cam);
+  NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
+
+int nerf_generate_rays_from_pixels_devcam(const int64_t* pixel_idx_dev, int64_t first_pixel, int64_t n,
+                                          const nerf_camera_t* cam_dev, float* ray_o_dev, float* ray_d_dev,
+                                          nerf_stream_t stream) {
+  NERF_CHECK_ARG(n >= 0, "nerf_generate_rays_from_pixels_devcam: negative ray count");
+  if (n == 0) return NERF_OK;
+  NERF_CHECK_ARG(cam_dev && ray_o_dev && ray_d_dev, "nerf_generate_rays_from_pixels_devcam: null pointer");
+  nerf_camera_t unused = {};
+  raygen_kernel<<<(unsigned)ceil_div64(n, 256 * kRaysPerThread), 256, 0, as_stream(stream)>>>(
+      nullptr, pixel_idx_dev, first_pixel, n, unused, cam_dev, ray_o_dev, ray_d_dev, aligned16(ray_o_dev, ray_d_dev));
   NERF_LAUNCH_CHECK();
   return NERF_OK;
 }

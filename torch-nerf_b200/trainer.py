@@ -57,8 +57,10 @@ class Trainer:
     def __init__(self, coarse: NeRF, fine: NeRF, num_samples_coarse: int = 64, num_samples_fine: int = 128,
                  num_pixels: int = 4096, t_near: float = 2.0, t_far: float = 6.0, project_to_ndc: bool = False,
                  init_lr: float = 5e-4, end_lr: float = 5e-5, num_iter: int = 300000, eps: float = 1e-8,
-                 precision: str = "bf16", rank: int = 0, world: int = 1, seed: int = 0):
+                 precision: str = "bf16", rank: int = 0, world: int = 1, seed: int = 0, use_graph: bool = True):
         from .engine import HotPathEngine
+
+        self.use_graph = bool(use_graph) and precision == "bf16"
 
         self.coarse, self.fine = coarse, fine
         self.engine = HotPathEngine(coarse, fine, num_samples_coarse, num_samples_fine, precision)
@@ -93,9 +95,15 @@ class Trainer:
         pix = self.select_pixels(camera.img_height, camera.img_width, epoch)
         lo, hi = shard_range(len(pix), self.rank, self.world)
         pix = pix[lo:hi]
-        tgt = pixel_gt.reshape(-1, 3)[pix.to(pixel_gt.device)].to(self.device, torch.float32, non_blocking=True).contiguous()
-        losses = self.engine.train_pixels(camera, pix.to(self.device, non_blocking=True), tgt, self.project_to_ndc,
-                                          loss_out=self._losses)
+        tgt = pixel_gt.reshape(-1, 3)[pix.to(pixel_gt.device)].to(torch.float32).contiguous()
+        if self.use_graph:
+            # the whole forward + backward replayed from one CUDA graph; pixel ids and colours are
+            # copied straight into the graph's static buffers
+            losses = self.engine.train_pixels_graph(camera, pix, tgt, self.project_to_ndc)
+        else:
+            losses = self.engine.train_pixels(camera, pix.to(self.device, non_blocking=True),
+                                              tgt.to(self.device, non_blocking=True), self.project_to_ndc,
+                                              loss_out=self._losses)
         allreduce_mean_(self.flat.grad, self.world, scale=False)  # the 1/world rides on the Adam kernel
         self.optimizer.step()
         self.scheduler.step()
