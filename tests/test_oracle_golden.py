@@ -177,3 +177,45 @@ def test_cdf_warp_scan_is_exactly_the_sequential_sum():
             scan[:, base:base + 32] = inc
             carry = inc[:, -1]
         assert np.array_equal(scan, seq)
+
+
+def test_blocked_sorting_network_of_the_fine_sampler():
+    """rays.cu warp_sort128_blocked, replayed in numpy stage by stage (same partner / mirror / keep-min rules): it must
+    sort any 128 values, duplicates included."""
+    rng = np.random.default_rng(0)
+    lanes = np.arange(32)
+
+    def cx(v, a, b):
+        lo, hi = np.minimum(v[:, a], v[:, b]), np.maximum(v[:, a], v[:, b])
+        v[:, a], v[:, b] = lo, hi
+
+    def network(v):
+        v = v.copy()
+        k = 2
+        while k <= 128:
+            j = k >> 1
+            while j > 0:
+                mirror = j == (k >> 1)
+                if j >= 4:
+                    lane_mask = ((k - 1) >> 2) if mirror else (j >> 2)
+                    keep_min = (lanes & (j >> 2)) == 0
+                    new = v.copy()
+                    for r in range(4):
+                        other = (v[:, r ^ 3] if mirror else v[:, r])[lanes ^ lane_mask]
+                        new[:, r] = np.where((v[:, r] > other) == keep_min, other, v[:, r])
+                    v = new
+                elif j == 2:
+                    for a, b in ([(0, 3), (1, 2)] if mirror else [(0, 2), (1, 3)]):
+                        cx(v, a, b)
+                else:
+                    cx(v, 0, 1)
+                    cx(v, 2, 3)
+                j >>= 1
+            k <<= 1
+        return v
+
+    for trial in range(300):
+        x = rng.random((32, 4)).astype(np.float32)
+        if trial % 3 == 0:
+            x = np.round(x * 8) / 8
+        assert np.array_equal(network(x).reshape(-1), np.sort(x.reshape(-1)))

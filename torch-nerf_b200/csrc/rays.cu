@@ -420,6 +420,50 @@ __device__ __forceinline__ void warp_bitonic_sort_regs(float (&v)[NSLOT]) {
   }
 }
 
+// Ascending sort of 128 floats held four per lane in BLOCKED order (element e = 4 * lane + slot).  It is the bitonic
+// network in its all-ascending form: the first step of every merge pairs e with its mirror image e ^ (k - 1) inside the
+// k-block, the remaining steps pair e with e ^ j, and the smaller value always goes to the smaller index.  Steps with
+// j < 4 stay inside the lane (13 of the 28 stages: two min/max pairs each, no shuffle, no select); the other 15 cost one
+// shuffle + compare + select per element.
+__device__ __forceinline__ void warp_sort128_blocked(float (&v)[4]) {
+  const int lane = lane_id();
+  auto cx = [&](int a, int b) {  // in-lane compare-exchange, a < b
+    const float lo = fminf(v[a], v[b]), hi = fmaxf(v[a], v[b]);
+    v[a] = lo, v[b] = hi;
+  };
+#pragma unroll
+  for (int k = 2; k <= 128; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const bool mirror = (j == (k >> 1));
+      if (j >= 4) {
+        const int lane_mask = mirror ? ((k - 1) >> 2) : (j >> 2);
+        const bool keep_min = (lane & (j >> 2)) == 0;  // this lane holds the smaller index of each pair
+        float other[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)  // a mirrored partner sits in the opposite slot: offer slot r ^ 3, receive the partner's
+          other[r] = __shfl_xor_sync(0xffffffffu, mirror ? v[r ^ 3] : v[r], lane_mask);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const bool take = (v[r] > other[r]) == keep_min;  // smaller index keeps the minimum (ties: same value either way)
+          v[r] = take ? other[r] : v[r];
+        }
+      } else if (j == 2) {
+        if (mirror) {  // k == 4: pairs (0,3) (1,2)
+          cx(0, 3);
+          cx(1, 2);
+        } else {
+          cx(0, 2);
+          cx(1, 3);
+        }
+      } else {  // j == 1 (k == 2: the mirror of e is e ^ 1 as well)
+        cx(0, 1);
+        cx(2, 3);
+      }
+    }
+  }
+}
+
 // Branch-free binary searches over power-of-two arrays, R independent keys per lane advanced in lock step (the loads
 // of the R searches overlap; no lane-dependent trip counts).
 // count[r] = number of elements of the ascending array a[0..N) that are < x[r] (strict) or <= x[r]
@@ -500,11 +544,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     const bool bad = (tc[0] > (lane == 31 ? first1 : nxt0)) || (lane < 31 && tc[1] > nxt1);
     if (__any_sync(0xffffffffu, bad)) warp_bitonic_sort_regs<2>(tc);
   }
-  warp_bitonic_sort_regs<4>(tf);
+  // which draw sits in which (lane, slot) is irrelevant before the sort: read the striped registers as blocked
+  warp_sort128_blocked(tf);
 #pragma unroll
   for (int r = 0; r < 2; ++r) sa[32 * r + lane] = tc[r];
-#pragma unroll
-  for (int r = 0; r < 4; ++r) sb[32 * r + lane] = tf[r];
+  *reinterpret_cast<float4*>(sb + 4 * lane) = make_float4(tf[0], tf[1], tf[2], tf[3]);
   __syncwarp();
   // merge (stratified_sampler.py:87-90 sorts the concatenation): ties put the coarse element first
   int below_c[2], below_f[4];
@@ -513,7 +557,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 #pragma unroll
   for (int r = 0; r < 2; ++r) ts[32 * r + lane + below_c[r]] = tc[r];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) ts[32 * r + lane + below_f[r]] = tf[r];
+  for (int r = 0; r < 4; ++r) ts[4 * lane + r + below_f[r]] = tf[r];
   __syncwarp();
   emit_samples(ts, s, ray, ray_o, ray_d, t_out, pts, dirs, delta, stage);
 }
