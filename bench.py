@@ -404,14 +404,14 @@ def run_b200(args):
         runs = [
             ("raygen_kernel", nr * 24,
              lambda: ck(lib.nerf_generate_rays_from_pixels(None, 0, nr, cam_s, P(ro), P(rd), st()), "raygen")),
-            ("sample_coarse_kernel", nr * SC * 12,
+            ("sample_coarse_flat_kernel", nr * SC * 12,
              lambda: ck(lib.nerf_sample_coarse(P(ro), P(rd), nr, SC, 2.0, 6.0, P(u_c), P(t_c), None, None, P(d_c), st()), "coarse")),
-            ("sample_fine_kernel", nr * (SC * 8 + SF * 8 + S * 8),
+            ("sample_fine_64_128_kernel", nr * (SC * 8 + SF * 8 + S * 8),
              lambda: ck(lib.nerf_sample_fine(P(ro), P(rd), nr, SC, SF, 2.0, 6.0, P(w_c), P(u_c), P(u1), P(u2), None, P(t_f), None,
                                              None, P(d_f), st()), "fine")),
-            ("composite_fwd_kernel", nr * S * 24 + nr * 12,
+            ("composite_fwd_reg_kernel<6>", nr * S * 24 + nr * 12,
              lambda: ck(lib.nerf_composite_fwd(P(sig), P(rad), P(d_f), None, nr, S, P(rgb_o), P(w_o), None, None, st()), "comp")),
-            ("composite_bwd_kernel", nr * S * 36 + nr * 12,
+            ("composite_bwd_reg_kernel<6>", nr * S * 36 + nr * 12,
              lambda: ck(lib.nerf_composite_bwd(P(sig), P(rad), P(d_f), P(g_rgb), None, nr, S, P(g_sig), P(g_rad), st()), "compb")),
         ]
         stages = []
