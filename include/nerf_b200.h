@@ -219,8 +219,10 @@ int nerf_debug_set_bwd_phases(int mask);
 int nerf_debug_set_wgrad_profile(unsigned long long* buf_dev);
 
 /* self test + rate probe of the CTA-pair MMA (tcgen05 cta_group::2, M = 256): a (256 x k), b (n x k) bf16 bits, d (256 x n)
- * fp32, all row-major; ts != 0 puts the A operand in tensor memory.  `pairs` clusters of two CTAs all compute the same
- * product; with iters > 0 each leader then times iters x (k/16) MMAs into cycles_dev[pair]. */
+ * fp32, all row-major; bit 0 of ts puts the A operand in tensor memory.  `pairs` clusters of two CTAs all compute the same
+ * product; with iters > 0 each leader then times iters x (k/16) MMAs into cycles_dev[pair].  With bit 1 of ts (n <= 128,
+ * iters > 0) BOTH CTAs of every pair issue pair MMAs, each into its own accumulator: cycles_dev[cta] for 2 x pairs
+ * entries, and d receives the accumulator the second CTA issued into. */
 int nerf_selftest_umma2(const uint16_t* a_dev, const uint16_t* b_dev, float* d_dev, int n, int k, int ts, int pairs, int iters,
                         unsigned long long* cycles_dev, nerf_stream_t stream);
 

@@ -142,7 +142,8 @@ __global__ void __launch_bounds__(128, 1) selftest_umma_kernel(const uint16_t* _
 // ------------------------------------------------------------------------------------------------
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
     selftest_umma2_kernel(const uint16_t* __restrict__ a, const uint16_t* __restrict__ b, float* __restrict__ d, int n, int k,
-                          int ts, int iters, unsigned long long* __restrict__ cycles) {
+                          int ts_mode, int iters, unsigned long long* __restrict__ cycles) {
+  const int ts = ts_mode & 1, both = (ts_mode >> 1) & 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar[2];
@@ -164,7 +165,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
   fence_proxy_async();
   if (threadIdx.x == 0) {
     mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
+    mbar_init(&bar[1], both ? 2 : 1);  // one multicast commit per issuing CTA
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc2(&tmem_slot, 512);
@@ -190,19 +191,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
     tc_fence_after();
   }
   const uint32_t idesc = make_idesc_bf16_m256((uint32_t)n);
-  auto issue_all = [&]() {
+  auto issue_all = [&](uint32_t acc) {
     for (int kk = 0; kk < k / 16; ++kk) {
       const uint64_t db = desc_kmajor(smem_u32(sB) + (kk / 4) * b_blk + (kk % 4) * 32);
       if (ts) {
-        umma2_bf16_ts(tmem_base, tmem_base + 256 + 8 * kk, db, idesc, kk > 0 ? 1u : 0u);
+        umma2_bf16_ts(acc, tmem_base + 256 + 8 * kk, db, idesc, kk > 0 ? 1u : 0u);
       } else {
         const uint64_t da = desc_kmajor(smem_u32(sA) + (kk / 4) * a_blk + (kk % 4) * 32);
-        umma2_bf16(tmem_base, da, db, idesc, kk > 0 ? 1u : 0u);
+        umma2_bf16(acc, da, db, idesc, kk > 0 ? 1u : 0u);
       }
     }
   };
   if (rank == 0 && threadIdx.x == 0) {
-    issue_all();
+    issue_all(tmem_base);
     umma2_commit(&bar[0], 3);
   }
   mbar_wait(&bar[0], 0);
@@ -219,14 +220,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
     __syncthreads();
     cluster_sync_all();
     tc_fence_after();
-    if (rank == 0 && threadIdx.x == 0) {
+    // both != 0: BOTH CTAs of the pair issue pair MMAs, each into its own accumulator (columns 128 * rank; n <= 128):
+    // every instruction costs its issuing thread the same ~100 cycles but feeds both SMs' tensor pipes
+    if (threadIdx.x == 0 && (rank == 0 || both)) {
+      const uint32_t acc = tmem_base + (both ? 128u * rank : 0u);
       const long long t0 = clock64();
-      for (int it = 0; it < iters; ++it) issue_all();
+      for (int it = 0; it < iters; ++it) issue_all(acc);
       umma2_commit(&bar[1], 3);
       mbar_wait(&bar[1], 0);
-      cycles[blockIdx.x / 2] = (unsigned long long)(clock64() - t0);
+      cycles[both ? blockIdx.x : blockIdx.x / 2] = (unsigned long long)(clock64() - t0);
     } else {
       mbar_wait(&bar[1], 0);
+    }
+    if (both) {  // the accumulator the SECOND CTA issued into goes back to d: the caller checks it like the first
+      tc_fence_after();
+      for (int c = 0; c < n / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + 128 + c * 32, v);
+        tmem_ld_wait();
+        for (int i = 0; i < 32; ++i) d[(size_t)(rank * 128 + row) * n + c * 32 + i] = __uint_as_float(v[i]);
+      }
     }
   }
   tc_fence_before();
@@ -389,7 +402,7 @@ int nerf_selftest_umma2(const uint16_t* a_dev, const uint16_t* b_dev, float* d_d
                         unsigned long long* cycles_dev, nerf_stream_t stream) {
   NERF_CHECK_ARG(a_dev && b_dev && d_dev, "nerf_selftest_umma2: null pointer");
   NERF_CHECK_ARG(n >= 32 && n <= 256 && n % 32 == 0 && k >= 64 && k <= 256 && k % 64 == 0 && pairs >= 1 && iters >= 0 &&
-                     (iters == 0 || cycles_dev),
+                     (iters == 0 || cycles_dev) && ts >= 0 && ts <= 3 && (!(ts & 2) || (n <= 128 && iters > 0)),
                  "nerf_selftest_umma2: n multiple of 32 in [32,256], k multiple of 64 in [64,256]");
   size_t smem = (size_t)128 * k * 2 + (size_t)(n / 2) * k * 2 + 1024;
   NERF_CUDA(cudaFuncSetAttribute(selftest_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
