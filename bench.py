@@ -369,6 +369,30 @@ def run_b200(args):
                   "finite": bool(torch.isfinite(img).all().item())}
         if sharded == 1:
             render["frame_ms_1gpu"] = frame_ms
+        # configs[4]: LLFF-shaped forward-facing view, 1008x756, NDC rays, near/far 0/1 (runner_utils.py:489-491), same
+        # sharding; two frames timed
+        if args.precision == "bf16":
+            lw, lh, lf = 1008, 756, 815.0
+            c2w = torch.eye(4)[:3, :4].clone()
+            c2w[:, 3] = torch.tensor([0.05, -0.02, 0.1])
+            cam_l = tn.PerspectiveCamera({"f_x": lf, "f_y": lf, "img_width": lw, "img_height": lh}, c2w, 0.0, 1.0)
+            lo_l, hi_l = shard_range(lw * lh, rank, world)
+            eng_render.render_frame(cam_l, True, lo_l, hi_l - lo_l)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            ev0.record()
+            for _ in range(2):
+                img_l = eng_render.render_frame(cam_l, True, lo_l, hi_l - lo_l)
+            ev1.record()
+            torch.cuda.synchronize()
+            llff_ms = ev0.elapsed_time(ev1) / 2
+            if world > 1:
+                tmax = torch.tensor([llff_ms], device=dev)
+                dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+                llff_ms = float(tmax.item())
+            render["llff_1008x756_ndc"] = {"frame_ms": llff_ms, "rays_per_s": lw * lh / (llff_ms * 1e-3),
+                                           "finite": bool(torch.isfinite(img_l).all().item())}
 
     # ---- HBM-bound stages: ray generation, sampling, compositing at the frame's ray count, each kernel timed
     #      alone with CUDA events; algorithmic bytes per unit as listed in DESIGN.md section 4
