@@ -435,7 +435,7 @@ def run_b200(args):
                                              None, P(d_f), st()), "fine")),
             ("composite_fwd_reg_kernel<6>", nr * S * 24 + nr * 12,
              lambda: ck(lib.nerf_composite_fwd(P(sig), P(rad), P(d_f), None, nr, S, P(rgb_o), P(w_o), None, None, st()), "comp")),
-            ("composite_bwd_reg_kernel<6>", nr * S * 36 + nr * 12,
+            ("composite_bwd_blk_kernel<6>", nr * S * 36 + nr * 12,
              lambda: ck(lib.nerf_composite_bwd(P(sig), P(rad), P(d_f), P(g_rgb), None, nr, S, P(g_sig), P(g_rad), st()), "compb")),
         ]
         stages = []

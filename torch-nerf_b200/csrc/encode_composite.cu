@@ -250,8 +250,8 @@ __global__ void __launch_bounds__(kCompWarps * 32)
 // K7 / K8 for rays of at most 32*G samples (G = 2, 4, 6, 8; the reference's 64 and 192 are G = 2 and 6).  Same
 // arithmetic as the chunk-walking kernels above; what changes is the memory schedule: a warp issues EVERY load of its
 // ray (sigma, delta, t, the 3*S radiance floats as consecutive 128-byte rows) before the first dependent instruction,
-// so ~3.8 KB per warp are in flight instead of one 640-byte chunk, and each input is read exactly once (the backward
-// no longer re-reads sigma/delta for its prefix pass).
+// so ~3.8 KB per warp are in flight instead of one 640-byte chunk, and each input is read exactly once.  The forward
+// keeps the samples striped over the lanes (chunk scans interleaved); the backward is the blocked kernel further down.
 // ------------------------------------------------------------------------------------------------
 // inclusive float64 scans of G independent 32-element chunks, interleaved so the G shuffle/add chains overlap
 template <int G>
@@ -267,20 +267,6 @@ __device__ __forceinline__ void chunk_scans_up(double (&inc)[G]) {
       if (lane >= d) inc[c] += up[c];
   }
 }
-template <int G>
-__device__ __forceinline__ void chunk_scans_down(double (&sfx)[G]) {
-  const int lane = lane_id();
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    double dn[G];
-#pragma unroll
-    for (int c = 0; c < G; ++c) dn[c] = shfl_down_f64(sfx[c], d);
-#pragma unroll
-    for (int c = 0; c < G; ++c)
-      if (lane + d < 32) sfx[c] += dn[c];
-  }
-}
-
 // Transmittance of every sample of the ray: x = sigma*delta (:41), float64 prefix sums rounded per element like torch's
 // cumsum, shifted to a true exclusive scan (:44-52).  The running sum across chunks is carry_c = carry_{c-1} + (chunk
 // c-1's total), the same additions the chunk-walking kernel makes.
@@ -367,85 +353,149 @@ __global__ void __launch_bounds__(kCompWarps * 32)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K8 in BLOCKED order: lane l owns the G consecutive samples [G l, G l + G) of its ray.  A striped backward (samples 32 c + lane, like the forward above) spends
+// the SM's data pipe on 64-bit shuffles (two float64 scans of G chunks = ~170 shuffles per ray, ncu: L1 pipe 80 % busy
+// at 61 % DRAM); here the scans are serial inside a lane plus ONE warp scan of the lane totals (~25 shuffles).  Global
+// accesses stay coalesced: rows are staged through shared memory, stored striped and read blocked (and the reverse for
+// the outputs) with one pad float per lane block so that the blocked accesses have an odd stride (no bank conflicts).
+// ------------------------------------------------------------------------------------------------
+template <int G>
+struct BlkLayout {
+  static constexpr int kS1 = G + 1;        // floats per lane block of a per-sample row (sigma, delta, g_w, g_sigma)
+  static constexpr int kS3 = 3 * G + 1;    // floats per lane block of the radiance / g_radiance row
+  static constexpr int kRow1 = 32 * kS1, kRow3 = 32 * kS3;
+  static constexpr int kWarpFloats = 2 * kRow1 + kRow3;  // sigma (reused for g_sigma) | delta (also g_w) | radiance
+  __device__ static __forceinline__ int pos1(int e) { return e + e / G; }          // striped element e -> padded slot
+  __device__ static __forceinline__ int pos3(int f) { return f + f / (3 * G); }
+};
+
 template <int G, int MB>
 __global__ void __launch_bounds__(kCompWarps * 32, MB)
-    composite_bwd_reg_kernel(const float* __restrict__ sigma, const float* __restrict__ radiance,
+    composite_bwd_blk_kernel(const float* __restrict__ sigma, const float* __restrict__ radiance,
                              const float* __restrict__ delta, const float* __restrict__ g_rgb,
                              const float* __restrict__ g_w_ext, int64_t n, int s, float* __restrict__ g_sigma,
                              float* __restrict__ g_radiance) {
-  __shared__ float stage_all[kCompWarps][96 * G];
+  using L = BlkLayout<G>;
+  __shared__ float stage_all[kCompWarps][L::kWarpFloats];
   const int warp = threadIdx.x >> 5, lane = lane_id();
-  float* stage = stage_all[warp];
+  float* s_sg = stage_all[warp];
+  float* s_dl = s_sg + L::kRow1;
+  float* s_rad = s_dl + L::kRow1;
   const int64_t ray = (int64_t)blockIdx.x * kCompWarps + warp;
   if (ray >= n) return;
   const float* sg_row = sigma + ray * s;
   const float* dl_row = delta + ray * s;
   const float* rad_row = radiance + ray * s * 3;
-  float x[G], dl[G], gw[G];
   {
-    float sg[G], rad[3 * G];
+    // every load of the ray first, then the striped -> blocked hand-over through shared memory
+    float sg[G], dl[G], ge[G], rad[3 * G];
 #pragma unroll
     for (int c = 0; c < G; ++c) {
-      const int i = 32 * c + lane;
-      const bool ok = i < s;
-      sg[c] = ok ? __ldg(sg_row + i) : 0.f;
-      dl[c] = ok ? __ldg(dl_row + i) : 0.f;
-      gw[c] = (g_w_ext && ok) ? __ldg(g_w_ext + ray * s + i) : 0.f;
+      const int e = 32 * c + lane;
+      const bool ok = e < s;
+      sg[c] = ok ? __ldg(sg_row + e) : 0.f;
+      dl[c] = ok ? __ldg(dl_row + e) : 0.f;
+      ge[c] = (g_w_ext && ok) ? __ldg(g_w_ext + ray * s + e) : 0.f;
     }
 #pragma unroll
     for (int k = 0; k < 3 * G; ++k) {
-      const int e = 32 * k + lane;
-      rad[k] = e < 3 * s ? __ldg(rad_row + e) : 0.f;
+      const int f = 32 * k + lane;
+      rad[k] = f < 3 * s ? __ldg(rad_row + f) : 0.f;
     }
 #pragma unroll
-    for (int k = 0; k < 3 * G; ++k) stage[32 * k + lane] = rad[k];
+    for (int c = 0; c < G; ++c) {
+      const int e = 32 * c + lane;
+      s_sg[L::pos1(e)] = __fmul_rn(sg[c], dl[c]);  // x = sigma * delta (:41)
+      s_dl[L::pos1(e)] = dl[c];
+    }
 #pragma unroll
-    for (int c = 0; c < G; ++c) x[c] = __fmul_rn(sg[c], dl[c]);
+    for (int k = 0; k < 3 * G; ++k) s_rad[L::pos3(32 * k + lane)] = rad[k];
+    __syncwarp();
+    // blocked reads
+    float x[G], dlb[G], gw[G];
+    const float gr = __ldg(g_rgb + 3 * ray), gg = __ldg(g_rgb + 3 * ray + 1), gb = __ldg(g_rgb + 3 * ray + 2);
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+      x[k] = s_sg[lane * L::kS1 + k];
+      dlb[k] = s_dl[lane * L::kS1 + k];
+      const float r = s_rad[lane * L::kS3 + 3 * k], g = s_rad[lane * L::kS3 + 3 * k + 1], b = s_rad[lane * L::kS3 + 3 * k + 2];
+      gw[k] = gr * r + gg * g + gb * b;
+    }
+    if (g_w_ext) {  // the external weight gradient goes through the x slots once x has been read
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < G; ++c) s_sg[L::pos1(32 * c + lane)] = ge[c];
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < G; ++k) gw[k] += s_sg[lane * L::kS1 + k];
+    }
+    // transmittance: float64 prefix of x inside the lane, one warp scan of the lane totals, every prefix rounded to
+    // float32 like torch's cumsum output, shifted to a true exclusive scan (:44-52)
+    double pre[G];
+    double run = 0.0;
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+      run += (double)x[k];
+      pre[k] = run;
+    }
+    double off = run;  // inclusive scan of the lane totals ...
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double up = shfl_up_f64(off, d);
+      if (lane >= d) off += up;
+    }
+    off = shfl_up_f64(off, 1);  // ... shifted: the sum of everything before this lane's first sample
+    if (lane == 0) off = 0.0;
+    float w[G], tnext[G];
+    double sfx[G];
+    float excl = (float)off;
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+      const bool ok = G * lane + k < s;
+      const float trans = expf(-excl);
+      const float ex = expf(-x[k]);
+      w[k] = ok ? __fmul_rn(trans, __fsub_rn(1.0f, ex)) : 0.f;
+      tnext[k] = trans * ex;
+      excl = (float)(off + pre[k]);
+    }
+    // exclusive suffix sums of g_w * w: inside the lane, then across the later lanes
+    double tail = 0.0;
+#pragma unroll
+    for (int k = G - 1; k >= 0; --k) {
+      sfx[k] = tail;
+      tail += (double)gw[k] * (double)w[k];
+    }
+    double later = tail;  // inclusive suffix scan of the lane totals
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double dn = shfl_down_f64(later, d);
+      if (lane + d < 32) later += dn;
+    }
+    later = shfl_down_f64(later, 1);
+    if (lane == 31) later = 0.0;
+    __syncwarp();  // all blocked reads are done: the staging rows now collect the outputs
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+      const float gx = (float)((double)gw[k] * (double)tnext[k] - (sfx[k] + later));
+      s_sg[lane * L::kS1 + k] = dlb[k] * gx;
+      s_rad[lane * L::kS3 + 3 * k] = w[k] * gr;
+      s_rad[lane * L::kS3 + 3 * k + 1] = w[k] * gg;
+      s_rad[lane * L::kS3 + 3 * k + 2] = w[k] * gb;
+    }
+    __syncwarp();
   }
-  const float gr = __ldg(g_rgb + 3 * ray), gg = __ldg(g_rgb + 3 * ray + 1), gb = __ldg(g_rgb + 3 * ray + 2);
-  __syncwarp();
-  float trans[G];
-  transmittance<G>(x, trans);
-  // per sample: w, T_{i+1} = T_i e^{-x_i}, g_w = g_rgb . c (+ external)
-  float w[G], tnext[G];
-  double sfx[G];
+  float* gs_row = g_sigma + ray * s;
+  float* gc_row = g_radiance + ray * s * 3;
 #pragma unroll
   for (int c = 0; c < G; ++c) {
-    const int i = 32 * c + lane;
-    const bool ok = i < s;
-    const float ex = expf(-x[c]);
-    w[c] = ok ? __fmul_rn(trans[c], __fsub_rn(1.0f, ex)) : 0.f;
-    tnext[c] = trans[c] * ex;
-    const float r = stage[3 * i], g = stage[3 * i + 1], b = stage[3 * i + 2];
-    gw[c] += gr * r + gg * g + gb * b;
-    sfx[c] = ok ? (double)gw[c] * (double)w[c] : 0.0;
+    const int e = 32 * c + lane;
+    if (e < s) gs_row[e] = s_sg[BlkLayout<G>::pos1(e)];
   }
-  __syncwarp();  // every lane has read its radiance: the staging rows now collect g_c = w * g_rgb
-  // exclusive suffix scans of gw*w (float64): inside the chunks, then the carry from the far end
-  chunk_scans_down<G>(sfx);
-  double suffix = 0.0;  // sum_{k > last element of this chunk} g_w_k w_k
-#pragma unroll
-  for (int c = G - 1; c >= 0; --c) {
-    const int i = 32 * c + lane;
-    const bool ok = i < s;
-    double sfx_excl = shfl_down_f64(sfx[c], 1);
-    if (lane == 31) sfx_excl = 0.0;
-    sfx_excl += suffix;
-    if (ok) {
-      const float gx = (float)((double)gw[c] * (double)tnext[c] - sfx_excl);
-      g_sigma[ray * s + i] = dl[c] * gx;
-    }
-    stage[3 * i] = w[c] * gr;
-    stage[3 * i + 1] = w[c] * gg;
-    stage[3 * i + 2] = w[c] * gb;
-    suffix += shfl_f64(sfx[c], 0);
-  }
-  __syncwarp();
-  float* dst = g_radiance + ray * s * 3;
 #pragma unroll
   for (int k = 0; k < 3 * G; ++k) {
-    const int e = 32 * k + lane;
-    if (e < 3 * s) dst[e] = stage[e];
+    const int f = 32 * k + lane;
+    if (f < 3 * s) gc_row[f] = s_rad[BlkLayout<G>::pos3(f)];
   }
 }
 
@@ -457,13 +507,14 @@ static void launch_composite_fwd_reg(const float* sigma, const float* radiance, 
       sigma, radiance, delta, t, n, s, rgb, w, depth, opacity);
 }
 template <int G>
-static void launch_composite_bwd_reg(const float* sigma, const float* radiance, const float* delta, const float* g_rgb,
+static void launch_composite_bwd_blk(const float* sigma, const float* radiance, const float* delta, const float* g_rgb,
                                      const float* g_w, int64_t n, int s, float* g_sigma, float* g_radiance,
                                      cudaStream_t stream) {
   // 6 CTAs per SM (80 registers per thread) measured best for 192 samples: 945 us at the unconstrained 95 registers,
   // 866 us at 80, 875 us at 64 (640 000 rays)
-  constexpr int kMinBlocks = G <= 6 ? 6 : 4;
-  composite_bwd_reg_kernel<G, kMinBlocks><<<(unsigned)ceil_div64(n, kCompWarps), kCompWarps * 32, 0, stream>>>(
+  // CTAs per SM measured on 192 samples (640 000 rays): 5 -> 778 us, 6 -> 768 us, 7 (72 registers) -> 704 us, 8 -> 797 us
+  constexpr int kMinBlocks = G <= 6 ? 7 : 4;
+  composite_bwd_blk_kernel<G, kMinBlocks><<<(unsigned)ceil_div64(n, kCompWarps), kCompWarps * 32, 0, stream>>>(
       sigma, radiance, delta, g_rgb, g_w, n, s, g_sigma, g_radiance);
 }
 
@@ -520,10 +571,10 @@ int nerf_composite_bwd(const float* sigma_dev, const float* radiance_dev, const 
                  "nerf_composite_bwd: null pointer");
   if (n == 0) return NERF_OK;
   cudaStream_t cs = as_stream(stream);
-  if (s <= 64) launch_composite_bwd_reg<2>(sigma_dev, radiance_dev, delta_dev, g_rgb_dev, g_w_dev, n, s, g_sigma_dev, g_radiance_dev, cs);
-  else if (s <= 128) launch_composite_bwd_reg<4>(sigma_dev, radiance_dev, delta_dev, g_rgb_dev, g_w_dev, n, s, g_sigma_dev, g_radiance_dev, cs);
-  else if (s <= 192) launch_composite_bwd_reg<6>(sigma_dev, radiance_dev, delta_dev, g_rgb_dev, g_w_dev, n, s, g_sigma_dev, g_radiance_dev, cs);
-  else if (s <= 256) launch_composite_bwd_reg<8>(sigma_dev, radiance_dev, delta_dev, g_rgb_dev, g_w_dev, n, s, g_sigma_dev, g_radiance_dev, cs);
+  if (s <= 64) launch_composite_bwd_blk<2>(sigma_dev, radiance_dev, delta_dev, g_rgb_dev, g_w_dev, n, s, g_sigma_dev, g_radiance_dev, cs);
+  else if (s <= 128) launch_composite_bwd_blk<4>(sigma_dev, radiance_dev, delta_dev, g_rgb_dev, g_w_dev, n, s, g_sigma_dev, g_radiance_dev, cs);
+  else if (s <= 192) launch_composite_bwd_blk<6>(sigma_dev, radiance_dev, delta_dev, g_rgb_dev, g_w_dev, n, s, g_sigma_dev, g_radiance_dev, cs);
+  else if (s <= 256) launch_composite_bwd_blk<8>(sigma_dev, radiance_dev, delta_dev, g_rgb_dev, g_w_dev, n, s, g_sigma_dev, g_radiance_dev, cs);
   else
     composite_bwd_kernel<<<(unsigned)ceil_div64(n, kCompWarps), kCompWarps * 32, 0, cs>>>(
         sigma_dev, radiance_dev, delta_dev, g_rgb_dev, g_w_dev, n, s, g_sigma_dev, g_radiance_dev);
