@@ -292,12 +292,21 @@ class HotPathEngine:
                 self._train_static(sg)
                 torch.cuda.synchronize(self.device)
                 l0 = self.launches
-                sg.graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(sg.graph, capture_error_mode="thread_local"):
-                    self._train_static(sg)
-                sg.launches = self.launches - l0
+                graph = torch.cuda.CUDAGraph()
+                try:
+                    with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                        self._train_static(sg)
+                    sg.graph = graph
+                    sg.launches = self.launches - l0
+                except RuntimeError as err:  # capture refused (e.g. another library touched the stream): stay eager
+                    import warnings
+
+                    warnings.warn(f"train_pixels_graph: CUDA graph capture failed, running eagerly ({err})")
+                    sg.graph = None
                 self.launches = l0
-            else:
+            elif sg.graph is not None:
                 sg.graph.replay()
                 self.launches += sg.launches
+            else:
+                self._train_static(sg)
         return sg.losses
