@@ -382,10 +382,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 // ------------------------------------------------------------------------------------------------
 // K3 fast path for the reference's default counts (64 coarse + 128 fine): the 256-wide bitonic network in shared
 // memory is what the general kernel spends its time on (36 stages, ~1700 warp instructions per ray).  Here the two sets
-// are sorted separately IN REGISTERS (element e of a set lives in slot e / 32 of lane e % 32; stages with a partner
-// distance below 32 are one shuffle + min/max, the others stay inside the lane), then merged by rank: every element's
-// final position is its own index plus a binary-search count in the other set.  Same multiset, same order, so the
-// output is bit-identical to the full sort.
+// are sorted separately IN REGISTERS (the stratified draws only if they are out of order, the importance draws four per
+// lane in blocked order) and then merged by ONE register bitonic merge of [fine ascending | +inf | coarse descending],
+// eight values per lane; in the fused form t and delta are stored straight from those registers.  Same multiset, so
+// the output is bit-identical to the full sort.
 // ------------------------------------------------------------------------------------------------
 template <int NSLOT>
 __device__ __forceinline__ void warp_bitonic_sort_regs(float (&v)[NSLOT]) {
@@ -464,35 +464,13 @@ __device__ __forceinline__ void warp_sort128_blocked(float (&v)[4]) {
   }
 }
 
-// Branch-free binary searches over power-of-two arrays, R independent keys per lane advanced in lock step (the loads
-// of the R searches overlap; no lane-dependent trip counts).
-// count[r] = number of elements of the ascending array a[0..N) that are < x[r] (strict) or <= x[r]
-template <int N, int R, bool kOrEqual>
-__device__ __forceinline__ void count_below(const float* a, const float (&x)[R], int (&count)[R]) {
-#pragma unroll
-  for (int r = 0; r < R; ++r) count[r] = 0;
-#pragma unroll
-  for (int step = N / 2; step > 0; step >>= 1) {
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const float v = a[count[r] + step - 1];
-      count[r] += (kOrEqual ? (v <= x[r]) : (v < x[r])) ? step : 0;
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < R; ++r) {  // the loop stops at min(count, N-1): one more probe tells N-1 from N
-    const float v = a[count[r]];
-    count[r] += (kOrEqual ? (v <= x[r]) : (v < x[r])) ? 1 : 0;
-  }
-}
-
 constexpr int kFastSc = 64, kFastSf = 128;
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     sample_fine_64_128_kernel(const float* __restrict__ ray_o, const float* __restrict__ ray_d, int64_t n, BinSpec bins,
                               float* __restrict__ weights, const float* __restrict__ u0, const float* __restrict__ u1,
                               const float* __restrict__ u2, int64_t* __restrict__ idx_out, float* __restrict__ t_out,
-                              float* __restrict__ pts, float* __restrict__ dirs, float* __restrict__ delta) {
+                              float* __restrict__ pts, float* __restrict__ dirs, float* __restrict__ delta, int vec_ok) {
   constexpr int sc = kFastSc, sf = kFastSf, s = sc + sf;
   // per warp: merged t (192) | sorted coarse (64) | sorted fine (128) | normalised weights (64) | cdf (64) | staging (96)
   extern __shared__ float smem[];
@@ -550,14 +528,68 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
   for (int r = 0; r < 2; ++r) sa[32 * r + lane] = tc[r];
   *reinterpret_cast<float4*>(sb + 4 * lane) = make_float4(tf[0], tf[1], tf[2], tf[3]);
   __syncwarp();
-  // merge (stratified_sampler.py:87-90 sorts the concatenation): ties put the coarse element first
-  int below_c[2], below_f[4];
-  count_below<sf, 2, false>(sb, tc, below_c);
-  count_below<sc, 4, true>(sa, tf, below_f);
+  // merge (stratified_sampler.py:87-90 sorts the concatenation) as ONE bitonic merge of 256 values held eight per
+  // lane in blocked order: [fine ascending (128) | +inf (64) | coarse descending (64)] is a bitonic sequence, so
+  // log2(256) = 8 compare-exchange stages sort it: five across lanes (shuffle), three inside the lane.
+  float v[8];
+  if (lane < 16) {
+    const float4 a = *reinterpret_cast<const float4*>(sb + 8 * lane), b = *reinterpret_cast<const float4*>(sb + 8 * lane + 4);
+    v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+  } else if (lane < 24) {
 #pragma unroll
-  for (int r = 0; r < 2; ++r) ts[32 * r + lane + below_c[r]] = tc[r];
+    for (int k = 0; k < 8; ++k) v[k] = INFINITY;
+  } else {
 #pragma unroll
-  for (int r = 0; r < 4; ++r) ts[4 * lane + r + below_f[r]] = tf[r];
+    for (int k = 0; k < 8; ++k) v[k] = sa[255 - 8 * lane - k];
+  }
+#pragma unroll
+  for (int j = 128; j >= 8; j >>= 1) {
+    const bool keep_min = (lane & (j >> 3)) == 0;
+    float other[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) other[k] = __shfl_xor_sync(0xffffffffu, v[k], j >> 3);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const bool take = (v[k] > other[k]) == keep_min;
+      v[k] = take ? other[k] : v[k];
+    }
+  }
+#pragma unroll
+  for (int j = 4; j >= 1; j >>= 1) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if ((k & j) == 0) {
+        const float lo = fminf(v[k], v[k | j]), hi = fmaxf(v[k], v[k | j]);
+        v[k] = lo, v[k | j] = hi;
+      }
+    }
+  }
+  // positions 8 lane + k < 192 (lanes 0..23) hold the sorted samples: the +inf padding ends up behind them
+  if (!pts && !dirs && vec_ok) {
+    // fused form: t and the forward differences (stratified_sampler.py:112-119) go out straight from the registers
+    const float nxt = __shfl_down_sync(0xffffffffu, v[0], 1);
+    if (lane < 24) {
+      float d[8];
+#pragma unroll
+      for (int k = 0; k < 7; ++k) d[k] = __fsub_rn(v[k + 1], v[k]);
+      d[7] = __fsub_rn(lane == 23 ? 1e8f : nxt, v[7]);
+      if (t_out) {
+        float4* dst = reinterpret_cast<float4*>(t_out + ray * s + 8 * lane);
+        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+      }
+      if (delta) {
+        float4* dst = reinterpret_cast<float4*>(delta + ray * s + 8 * lane);
+        dst[0] = make_float4(d[0], d[1], d[2], d[3]);
+        dst[1] = make_float4(d[4], d[5], d[6], d[7]);
+      }
+    }
+    return;
+  }
+  if (lane < 24) {
+    *reinterpret_cast<float4*>(ts + 8 * lane) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(ts + 8 * lane + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
   __syncwarp();
   emit_samples(ts, s, ray, ray_o, ray_d, t_out, pts, dirs, delta, stage);
 }
@@ -694,7 +726,7 @@ int nerf_sample_fine(const float* ray_o_dev, const float* ray_d_dev, int64_t n, 
     const size_t smem_fast = sizeof(float) * kWarpsPerBlock * ((kFastSc + kFastSf) * 2 + 2 * kFastSc + 96);
     sample_fine_64_128_kernel<<<(unsigned)ceil_div64(n, kWarpsPerBlock), kWarpsPerBlock * 32, smem_fast, as_stream(stream)>>>(
         ray_o_dev, ray_d_dev, n, make_bin_spec(t_near, t_far, num_coarse), weights_dev, u0_dev, u1_dev, u2_dev, idx_dev, t_dev,
-        pts_dev, dirs_dev, delta_dev);
+        pts_dev, dirs_dev, delta_dev, aligned16(t_dev, delta_dev));
     NERF_LAUNCH_CHECK();
     return NERF_OK;
   }
