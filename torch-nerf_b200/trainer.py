@@ -12,9 +12,8 @@ A profile of the captured step (tools/prof_gaps.py) shows 17 us of GPU idle time
 wrapped in a CUDA graph: there is no launch gap left to remove."""
 from __future__ import annotations
 
-from typing import Dict, Iterable, Optional, Tuple
+from typing import Dict, Iterable, Tuple
 
-import numpy as np
 import torch
 
 from .cameras import PerspectiveCamera
