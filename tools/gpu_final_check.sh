@@ -1,3 +1,6 @@
+#!/bin/bash
+# Short end-of-session check on a B200 box: all GPU tests, smoke, stage timings, the default bench line, the two launch
+# lists and one ncu capture of the fine sampler (a subset of tools/gpu_evidence.sh).
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -q -m gpu -p no:cacheprovider 2>&1 | tail -2
 timeout 200 python __graft_entry__.py --smoke 2>&1 | tail -1
