@@ -79,6 +79,26 @@ def test_raygen_full_frame_matches_oracle(tn):
     assert np.array_equal(b.ray_origin.cpu().numpy(), o)
 
 
+def test_raygen_frame_sized_launch_matches_oracle(tn):
+    """>= 2^18 rays take the four-rays-per-thread kernel with 16-byte stores (smaller launches: one ray per thread); also an
+    odd count and an unaligned output view, which must fall back to scalar stores."""
+    h, w = 601, 603
+    focal = orc.blender_focal(w)
+    c2w = orc.pose_spherical(-71.0, -25.0, 4.0)
+    cam = blender_camera(tn, h, w, focal, c2w)
+    o, d = orc.generate_rays(orc.screen_coords(h, w), orc.make_intrinsic(focal, focal, w, h), c2w, 2.0, h, w, False)
+    b = tn.StratifiedSampler().generate_rays_from_pixels(None, cam, False, first_pixel=0, count=h * w)
+    np.testing.assert_allclose(b.ray_dir.cpu().numpy(), d, rtol=1e-6, atol=1e-7)
+    assert np.array_equal(b.ray_origin.cpu().numpy(), o)
+    lib = tn._lib.load()
+    n = h * w
+    buf_o = torch.zeros(3 * n + 1, device="cuda")
+    buf_d = torch.zeros(3 * n + 1, device="cuda")
+    tn._lib.check(lib.nerf_generate_rays_from_pixels(None, 0, n, cam.pack(False), tn._lib.c_void_p(buf_o.data_ptr() + 4),
+                                                     tn._lib.c_void_p(buf_d.data_ptr() + 4), tn._lib.stream()), "raygen")
+    assert torch.equal(buf_d[1:].view(n, 3), b.ray_dir) and torch.equal(buf_o[1:].view(n, 3), b.ray_origin)
+
+
 # ------------------------------------------------------------------------------------------------ K2 / K3
 def test_coarse_sampling_bit_exact(tn):
     g = load_golden("coarse.npz")

@@ -19,7 +19,8 @@ namespace nerf {
 // ------------------------------------------------------------------------------------------------
 // K1
 // ------------------------------------------------------------------------------------------------
-constexpr int kRaysPerThread = 4;  // 4 rays = 12 floats = three 16-byte stores per output
+// kRPT rays per thread: 4 rays = 12 floats = three 16-byte stores per output (frame-sized launches); small training
+// batches use one ray per thread so that a 4096-ray launch still fills more than a handful of warps
 
 __device__ __forceinline__ void one_ray(const int64_t* __restrict__ coords, const int64_t* __restrict__ pix,
                                         int64_t first_pixel, int64_t i, const nerf_camera_t& cam, float* o, float* d) {
@@ -70,6 +71,7 @@ __device__ __forceinline__ void one_ray(const int64_t* __restrict__ coords, cons
 
 // `cam_dev` != null: the camera is read from device memory (a captured CUDA graph replays with whatever camera
 // nerf_upload_camera put there); otherwise it travels by value in the launch parameters.
+template <int kRPT>
 __global__ void __launch_bounds__(256) raygen_kernel(const int64_t* __restrict__ coords,
                                                       const int64_t* __restrict__ pix, int64_t first_pixel,
                                                       int64_t n, nerf_camera_t cam_arg,
@@ -77,12 +79,12 @@ __global__ void __launch_bounds__(256) raygen_kernel(const int64_t* __restrict__
                                                       float* __restrict__ ray_o, float* __restrict__ ray_d, int vec_ok) {
   nerf_camera_t cam = cam_arg;
   if (cam_dev != nullptr) cam = *cam_dev;
-  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * kRaysPerThread;
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * kRPT;
   if (i0 >= n) return;
-  if (vec_ok && i0 + kRaysPerThread <= n) {
-    float o[3 * kRaysPerThread], d[3 * kRaysPerThread];
+  if (kRPT == 4 && vec_ok && i0 + kRPT <= n) {
+    float o[3 * kRPT], d[3 * kRPT];
 #pragma unroll
-    for (int r = 0; r < kRaysPerThread; ++r) one_ray(coords, pix, first_pixel, i0 + r, cam, o + 3 * r, d + 3 * r);
+    for (int r = 0; r < kRPT; ++r) one_ray(coords, pix, first_pixel, i0 + r, cam, o + 3 * r, d + 3 * r);
     float4* dst_o = reinterpret_cast<float4*>(ray_o + 3 * i0);  // 48-byte slabs of a 16-byte aligned array
     float4* dst_d = reinterpret_cast<float4*>(ray_d + 3 * i0);
 #pragma unroll
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(256) raygen_kernel(const int64_t* __restrict__
       dst_d[k] = make_float4(d[4 * k], d[4 * k + 1], d[4 * k + 2], d[4 * k + 3]);
     }
   } else {
-    for (int64_t i = i0; i < min(i0 + kRaysPerThread, n); ++i) {
+    for (int64_t i = i0; i < min(i0 + kRPT, n); ++i) {
       float o[3], d[3];
       one_ray(coords, pix, first_pixel, i, cam, o, d);
 #pragma unroll
@@ -598,6 +600,15 @@ static int aligned16(const void* a, const void* b) {
   return (((uintptr_t)a | (uintptr_t)b) & 15) == 0;
 }
 
+static void launch_raygen(const int64_t* coords, const int64_t* pix, int64_t first_pixel, int64_t n, const nerf_camera_t& cam,
+                          const nerf_camera_t* cam_dev, float* ray_o, float* ray_d, cudaStream_t stream) {
+  if (n >= (int64_t)1 << 18)
+    raygen_kernel<4><<<(unsigned)ceil_div64(n, 256 * 4), 256, 0, stream>>>(coords, pix, first_pixel, n, cam, cam_dev, ray_o, ray_d,
+                                                                         aligned16(ray_o, ray_d));
+  else
+    raygen_kernel<1><<<(unsigned)ceil_div64(n, 256), 256, 0, stream>>>(coords, pix, first_pixel, n, cam, cam_dev, ray_o, ray_d, 0);
+}
+
 static int next_pow2(int v) {
   int p = 1;
   while (p < v) p <<= 1;
@@ -615,9 +626,7 @@ int nerf_generate_rays(const int64_t* coords_dev, int64_t n, const nerf_camera_t
   NERF_CHECK_ARG(n >= 0, "nerf_generate_rays: negative ray count");
   if (n == 0) return NERF_OK;
   NERF_CHECK_ARG(cam && coords_dev && ray_o_dev && ray_d_dev, "nerf_generate_rays: null pointer");
-  raygen_kernel<<<(unsigned)ceil_div64(n, 256 * kRaysPerThread), 256, 0, as_stream(stream)>>>(coords_dev, nullptr, 0, n, *cam, nullptr,
-                                                                             ray_o_dev, ray_d_dev,
-                                                                             aligned16(ray_o_dev, ray_d_dev));
+  launch_raygen(coords_dev, nullptr, 0, n, *cam, nullptr, ray_o_dev, ray_d_dev, as_stream(stream));
   NERF_LAUNCH_CHECK();
   return NERF_OK;
 }
@@ -629,9 +638,7 @@ int nerf_generate_rays_from_pixels(const int64_t* pixel_idx_dev, int64_t first_p
   if (n == 0) return NERF_OK;
   NERF_CHECK_ARG(cam && ray_o_dev && ray_d_dev, "nerf_generate_rays_from_pixels: null pointer");
   NERF_CHECK_ARG(cam->img_w > 0 && cam->img_h > 0, "nerf_generate_rays_from_pixels: bad image size");
-  raygen_kernel<<<(unsigned)ceil_div64(n, 256 * kRaysPerThread), 256, 0, as_stream(stream)>>>(nullptr, pixel_idx_dev, first_pixel, n,
-                                                                             *cam, nullptr, ray_o_dev, ray_d_dev,
-                                                                             aligned16(ray_o_dev, ray_d_dev));
+  launch_raygen(nullptr, pixel_idx_dev, first_pixel, n, *cam, nullptr, ray_o_dev, ray_d_dev, as_stream(stream));
   NERF_LAUNCH_CHECK();
   return NERF_OK;
 }
@@ -652,8 +659,7 @@ int nerf_generate_rays_from_pixels_devcam(const int64_t* pixel_idx_dev, int64_t 
   if (n == 0) return NERF_OK;
   NERF_CHECK_ARG(cam_dev && ray_o_dev && ray_d_dev, "nerf_generate_rays_from_pixels_devcam: null pointer");
   nerf_camera_t unused = {};
-  raygen_kernel<<<(unsigned)ceil_div64(n, 256 * kRaysPerThread), 256, 0, as_stream(stream)>>>(
-      nullptr, pixel_idx_dev, first_pixel, n, unused, cam_dev, ray_o_dev, ray_d_dev, aligned16(ray_o_dev, ray_d_dev));
+  launch_raygen(nullptr, pixel_idx_dev, first_pixel, n, unused, cam_dev, ray_o_dev, ray_d_dev, as_stream(stream));
   NERF_LAUNCH_CHECK();
   return NERF_OK;
 }
