@@ -219,3 +219,34 @@ def test_blocked_sorting_network_of_the_fine_sampler():
         if trial % 3 == 0:
             x = np.round(x * 8) / 8
         assert np.array_equal(network(x).reshape(-1), np.sort(x.reshape(-1)))
+
+
+def test_blocked_transmittance_scan_rounds_like_the_sequential_cumsum():
+    """encode_composite.cu composite_bwd_blk_kernel sums x = sigma*delta in float64 inside a lane (G consecutive samples),
+    scans the lane totals across the warp and rounds every prefix to float32.  torch's cumsum is a sequential float64
+    sum rounded per element; the two associations differ by ~1e-16 relative before the float32 rounding, so the rounded
+    prefixes must agree everywhere except for (at most) isolated last-bit ties."""
+    rng = np.random.default_rng(9)
+    n, g = 2048, 6
+    s = 32 * g
+    sigma = np.maximum(rng.normal(size=(n, s)) * 3.0, 0).astype(np.float32)
+    t = np.sort(2.0 + 4.0 * rng.random((n, s)), axis=-1).astype(np.float32)
+    delta = np.diff(np.concatenate([t, np.full((n, 1), 1e8, np.float32)], -1), axis=-1).astype(np.float32)
+    x = (sigma * delta).astype(np.float32)
+    seq = np.cumsum(x.astype(np.float64), axis=-1).astype(np.float32)
+    xb = x.astype(np.float64).reshape(n, 32, g)
+    pre = np.cumsum(xb, axis=-1)                       # serial inside a lane
+    tot = pre[:, :, -1].copy()
+    inc = tot.copy()
+    d = 1
+    while d < 32:                                      # Hillis-Steele over the lane totals
+        up = np.zeros_like(inc)
+        up[:, d:] = inc[:, :-d]
+        inc = inc + up
+        d *= 2
+    off = np.concatenate([np.zeros((n, 1)), inc[:, :-1]], axis=-1)
+    blk = (off[:, :, None] + pre).reshape(n, s).astype(np.float32)
+    mism = blk != seq
+    assert mism.mean() < 1e-5
+    if mism.any():
+        assert np.all(np.abs(blk[mism] - seq[mism]) <= np.spacing(np.abs(seq[mism])))
