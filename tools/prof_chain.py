@@ -34,6 +34,11 @@ if "--micro" in sys.argv:
     for mode, n in ((33, 128), (33, 64), (32, 128)):
         m, _ = rate(148, 2000, n, mode)
         print(f"two issuer warps, own accumulators, mode={'SS' if (mode & 1) == 0 else 'TS'} N={n:3d}: {m / 2:6.1f} cycles/MMA aggregate ({m:6.1f} per issuer)")
+    for mode, n in ((256, 128), (257, 128), (257 | 32, 128), (257, 256)):
+        m, _ = rate(148, 2000, n, mode)
+        two = bool(mode & 32)
+        print(f"mma M=64 mode={'TS' if mode & 1 else 'SS'} N={n:3d}{' two issuers' if two else ''}: {m / (2 if two else 1):6.1f} cycles/MMA"
+              f"{' aggregate' if two else ''} (an M=128 instruction of this N: {128 * n / 256:.0f} pipe cycles)")
     if "--short" in sys.argv:
         sys.exit(0)
     for w in (1, 4, 8, 16):

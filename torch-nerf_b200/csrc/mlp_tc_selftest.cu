@@ -282,7 +282,9 @@ __global__ void __launch_bounds__(640, 1) mma_rate_kernel(int iters, int n, int 
     // issue pattern of the chain kernels: the whole warp runs the loop, one elected lane issues.  mode bit 5: warp 1
     // is a second issuer working on its own accumulator (columns [128,256)) and its own completion barrier
     const bool leader = elect_one();
-    const uint32_t idesc = make_idesc_bf16((uint32_t)n, false, false);
+    // mode bit 8: M = 64 instructions (same descriptor with the M field halved; the data is not checked here)
+    const uint32_t idesc = (mode & 256) ? ((make_idesc_bf16((uint32_t)n, false, false) & ~(0x1fu << 24)) | ((64u >> 4) << 24))
+                                        : make_idesc_bf16((uint32_t)n, false, false);
     const uint64_t da = desc_kmajor(smem_u32(smem));
     const uint64_t db = desc_kmajor(smem_u32(smem) + 16384);
     uint64_t* done = warp == 0 ? &bar : &bar2[0];
@@ -413,7 +415,7 @@ int nerf_selftest_umma2(const uint16_t* a_dev, const uint16_t* b_dev, float* d_d
 
 int nerf_selftest_mma_rate(int blocks, int iters, int n, int mode, int bg_warps, int bg_iters, int bg_store,
                            unsigned long long* cycles_dev, nerf_stream_t stream) {
-  NERF_CHECK_ARG(cycles_dev && blocks > 0 && iters >= 0 && n >= 16 && n <= 256 && n % 16 == 0 && mode >= 0 && mode < 256 &&
+  NERF_CHECK_ARG(cycles_dev && blocks > 0 && iters >= 0 && n >= 16 && n <= 256 && n % 16 == 0 && mode >= 0 && mode < 512 &&
                      bg_warps >= 0 && bg_warps <= 16 && bg_iters >= 0,
                  "nerf_selftest_mma_rate: bad arguments");
   const size_t smem = 16384 + 32768 + 1024;
