@@ -31,6 +31,18 @@ FLOP_TRAIN_PER_EVAL = 3489024
 METRIC = "train rays/s (64+128 samples, fwd+bwd); 800x800 render ms @1/2/4/8 B200"
 
 
+def recorded_traffic(kernel, rows):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` on `rows` rows, as captured with
+    `ncu --set full` and recorded in profiles/traffic.json; None when no capture of exactly this shape exists."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    for rec in json.load(open(path)).get(kernel, []):
+        if rec.get("rows") == rows:
+            return rec.get("dram_bytes")
+    return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -123,9 +135,10 @@ class ClockSampler:
                 "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.samples), "source": self.source}
 
 
-# ------------------------------------------------------------------------------------------------ CPU baseline (oracle port)
+# ------------------------------------------------------------------------------------------------ reference arms
 def cpu_train_step_rays_per_s(rays, reps, seed=0):
-    """Times the oracle's training iteration (train.py:130-218 restated in numpy) on the host cores."""
+    """Fallback CPU baseline when baseline/_ref is not staged: the oracle's training iteration (train.py:130-218
+    restated in numpy) on the host cores."""
     from oracle import nerf_oracle as orc
 
     rng = np.random.default_rng(seed)
@@ -144,29 +157,169 @@ def cpu_train_step_rays_per_s(rays, reps, seed=0):
     return rays / float(np.median(times)), float(np.median(times))
 
 
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def _ref_scene(img):
+    import torch
+
+    focal = blender_focal(img)
+    intr = {"f_x": focal, "f_y": focal, "img_width": img, "img_height": img}
+    return intr, pose_spherical(30.0, -30.0, 4.0)
+
+
+def ref_train_rays_per_s(device, rays, steps, warmup, threads=None):
+    """The UNMODIFIED reference (baseline/_ref via baseline/ref_harness.py) running train.py:130-218 on `device`:
+    median seconds per step over `steps` steps of `rays` rays of an 800x800 camera.  CPU: wall clock; CUDA: events."""
+    import torch
+
+    from baseline import ref_harness as rh
+
+    if threads is not None:
+        torch.set_num_threads(threads)
+    sess = rh.RefSession(device)
+    intr, c2w = _ref_scene(IMG)
+    gt = torch.rand(IMG * IMG, 3)
+    cuda = torch.device(device).type == "cuda"
+    times = []
+    for i in range(warmup + steps):
+        if cuda:
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            sess.train_step(gt, intr, c2w, 2.0, 6.0, rays)
+            e1.record()
+            torch.cuda.synchronize()
+            dt = e0.elapsed_time(e1) * 1e-3
+        else:
+            t0 = time.perf_counter()
+            sess.train_step(gt, intr, c2w, 2.0, 6.0, rays)
+            dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    med = float(np.median(times))
+    return rays / med, med
+
+
+def ref_render_ms(device, img, reps, warmup, threads=None):
+    """The unmodified reference running render.py:58-107 (coarse + fine, num_ray_batch = H*W // 4096) on `device`."""
+    import torch
+
+    from baseline import ref_harness as rh
+
+    if threads is not None:
+        torch.set_num_threads(threads)
+    sess = rh.RefSession(device)
+    intr, c2w = _ref_scene(img)
+    cuda = torch.device(device).type == "cuda"
+    times = []
+    for i in range(warmup + reps):
+        if cuda:
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = sess.render_frame(intr, c2w, 2.0, 6.0, (img, img))
+        if cuda:
+            torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    del out
+    return float(np.median(times)) * 1e3
+
+
+def cpu_baseline_block(quick):
+    """cpu_baseline of the bench line: the reference's own CPU path on the box's host cores, bounded (10-30 s)."""
+    from baseline import ref_harness as rh
+
+    cores = host_cores()
+    ok, why = rh.available()
+    if ok:
+        rays, steps = 1024, (2 if quick else 3)
+        rps, med = ref_train_rays_per_s("cpu", rays, steps, 1, threads=cores)
+        return {"value": rps, "unit": "rays/s", "cores": cores, "kind": "reference", "ms_per_step": med * 1e3,
+                "sample": f"{steps} x {rays}-ray training steps (+1 warm-up) of the unmodified reference modules "
+                          f"(baseline/_ref: VolumeRenderer.render_scene coarse+fine, MSE, backward, Adam) on CPU, "
+                          f"torch.set_num_threads({cores}), median; rays/s scales linearly to the 4096-ray batch"}
+    rps, med = cpu_train_step_rays_per_s(256, 3)
+    return {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port", "ms_per_step": med * 1e3,
+            "sample": f"3 x 256-ray training iterations of the oracle (numpy port; {why}), median"}
+
+
 def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path on the host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rays = 256
-    cores = os.cpu_count() or 1
-    for _ in range(max(1, min(args.warmup, 1))):
-        cpu_train_step_rays_per_s(rays, 1)
-    steps = max(1, min(args.steps, 5))
+    from baseline import ref_harness as rh
+
+    cores = host_cores()  # torchrun exports OMP_NUM_THREADS=1: thread counts are set explicitly below
+    ok, why = rh.available()
     t0 = time.perf_counter()
-    rps, med = cpu_train_step_rays_per_s(rays, steps)
+    steps = max(1, min(args.steps, 4))
+    extra = {}
+    if ok:
+        rays = 1024
+        rps, med = ref_train_rays_per_s("cpu", rays, steps, max(1, min(args.warmup, 1)), threads=cores)
+        kind = "reference"
+        sample = (f"{steps} x {rays}-ray training steps of the unmodified reference modules (baseline/_ref) on CPU, "
+                  f"torch.set_num_threads({cores}), median")
+        if not args.quick:
+            # BASELINE.md section 3: the reference's own single-thread setting (runner_utils.py:427) and config C1
+            rps1, med1 = ref_train_rays_per_s("cpu", rays, 1, 0, threads=1)
+            c1_all = ref_render_ms("cpu", 100, 2, 0, threads=cores)
+            c1_one = ref_render_ms("cpu", 100, 1, 0, threads=1)
+            extra = {"train_1_thread": {"value": rps1, "unit": "rays/s", "cores": 1, "ms_per_step": med1 * 1e3,
+                                        "sample": f"1 x {rays}-ray training step, torch.set_num_threads(1)"},
+                     "c1_render_100x100": {"all_cores_ms": c1_all, "one_thread_ms": c1_one, "cores": cores,
+                                           "sample": "100x100 frame, 64 + (64+128) samples, num_ray_batch 2 (render.py:58-107); "
+                                                     "median of 2 frames (all cores), 1 frame (1 thread)"}}
+            import torch
+
+            torch.set_num_threads(cores)
+    else:
+        rays = 256
+        rps, med = cpu_train_step_rays_per_s(rays, steps)
+        kind = "port"
+        sample = f"{steps} x {rays}-ray training iterations (oracle numpy port: {why})"
     line = {
         "impl": "reference", "metric": METRIC, "value": rps, "unit": "rays/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": 1, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"train step, {rays}-ray sample of the 4096-ray batch, 800x800 lego-shaped camera, 64+128 samples, CPU",
+        "config": {"workload": f"train step (coarse 64 + fine 64+128, fwd+bwd, Adam), {rays}-ray sample of the {args.rays}-ray "
+                               f"batch, lego-shaped synthetic scene, 800x800 cameras, near/far 2/6, reference CPU path",
                    "rays_per_step": rays},
-        "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} x {rays}-ray training iterations (oracle numpy port of the reference path, BLAS threads = all cores)"},
+        "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": cores, "kind": kind, "sample": sample, **extra},
         "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0,
     }
     print(json.dumps(line))
+
+
+def reference_gpu_block(dev, n_rays):
+    """Same-box comparator: the unmodified reference modules on torch-CUDA on this
+    B200 -- cuBLAS fp32 GEMMs + ATen elementwise kernels + autograd, exactly what a user of the reference runs today."""
+    import torch
+
+    from baseline import ref_harness as rh
+
+    ok, why = rh.available()
+    if not ok:
+        return {"unavailable": why}
+    out = {"impl": "unmodified reference modules (baseline/_ref) on torch-CUDA, fp32 (TF32 off = torch default)",
+           "torch": torch.__version__}
+    with torch.cuda.device(dev):
+        rps, med = ref_train_rays_per_s(dev, n_rays, 5, 2)
+        out["train"] = {"rays_per_step": n_rays, "ms_per_step": med * 1e3, "rays_per_s": rps,
+                        "sample": "median of 5 steps after 2 warm-ups, CUDA events around train.py:130-218"}
+        torch.cuda.empty_cache()
+        out["c1_render_100x100_ms"] = ref_render_ms(dev, 100, 3, 1)
+        out["render_800x800_ms"] = ref_render_ms(dev, IMG, 1, 1)
+        torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
@@ -308,7 +461,7 @@ def run_b200(args):
                                                         P(sig), P(rgb), None, tn._lib.stream()), "fwd")
             sec = timed_kernel(k_fwd)
             ach = m * FLOP_FWD_PER_EVAL / sec / 1e12
-            roof_mlp = {"bound": "tensor", "kernel": "mlp_fwd_kernel (tcgen05 forward chain, 786432 rows, inference form)",
+            roof_mlp = {"bound": "tensor", "kernel": f"mlp_fwd_kernel (tcgen05 forward chain, {m} rows, inference form)",
                         "achieved": ach, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "traffic": None,
                         "peak_source": pk["src"] + " (burst: kernel timed alone)", "launch_ms": sec * 1e3}
             # wgrad alone: fill cache + scratch with one full forward/backward, then re-run only the wgrad phase
@@ -321,19 +474,19 @@ def run_b200(args):
             tn._lib.check(lib.nerf_mlp_bf16_forward(P(packed, torch.uint8), None, None, P(ray_o), P(ray_d), P(t), SC + SF, m,
                                                     P(sig), P(rgb), P(cache, torch.uint8), tn._lib.stream()), "fwd-train")
 
-            def k_bwd():
-                tn._lib.check(lib.nerf_mlp_bf16_backward(P(packed, torch.uint8), P(cache, torch.uint8), P(rgb), m, P(g_s), P(g_c),
-                                                         garr, P(scratch, torch.uint8), tn._lib.stream()), "bwd")
-            k_bwd()
-            lib.nerf_debug_set_bwd_phases(4)
-            sec_w = timed_kernel(k_bwd)
-            lib.nerf_debug_set_bwd_phases(7)
             tiles = (m + 127) // 128
+
+            def k_bwd(phases=7):
+                tn._lib.check(lib.nerf_mlp_bf16_backward_part(P(packed, torch.uint8), P(cache, torch.uint8), P(rgb), m, P(g_s),
+                                                              P(g_c), garr, P(scratch, torch.uint8), phases, 0, tiles, 0,
+                                                              tn._lib.stream()), "bwd")
+            k_bwd()
+            sec_w = timed_kernel(lambda: k_bwd(4))  # the weight-gradient kernel alone, on the scratch a full backward filled
             alg_bytes = tiles * (83 * 16384 + 2 * 128 * 16)  # 83 blocks of 16 KB (G and X tile images) + head gradients per tile
             ach_w = alg_bytes / sec_w / 1e9
-            roof = {"bound": "hbm", "kernel": "mlp_wgrad_kernel (split-K tcgen05 weight gradients, 786432 rows)",
+            roof = {"bound": "hbm", "kernel": f"mlp_wgrad_kernel (split-K tcgen05 weight gradients, {m} rows)",
                     "achieved": ach_w, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_w / pk["hbm_gbs"],
-                    "traffic": 8.3834e9,  # dram__bytes_read + write of one launch, ncu --set full (profiles/r01_ncu_wgrad.txt)
+                    "traffic": recorded_traffic("mlp_wgrad_kernel", m),  # dram bytes of one launch from ncu --set full, or null
                     "algorithmic_bytes": alg_bytes, "peak_source": pk["src"] + " (burst: kernel timed alone)",
                     "peak_note": "the peak is a copy (read+write) figure; this kernel only reads, and a read-only stream "
                                  "measures 6.7 TB/s on the same pool (tools/prof_store.py), hence frac slightly above 1",
@@ -450,16 +603,23 @@ def run_b200(args):
 
     if rank == 0:
         cpu = None
+        ref_gpu = None
         if world == 1 and not args.no_cpu_baseline:
-            rps, med = cpu_train_step_rays_per_s(256, 3)
-            cpu = {"value": rps, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
-                   "sample": "3 x 256-ray training iterations of the oracle (numpy port of the reference CPU path), median"}
+            cpu = cpu_baseline_block(args.quick)
+        if world == 1 and not args.no_reference_gpu:
+            try:
+                ref_gpu = reference_gpu_block(dev, n_rays)
+                ref_gpu["speedup_train"] = value / ref_gpu["train"]["rays_per_s"]
+                if render is not None:
+                    ref_gpu["speedup_render_800x800"] = ref_gpu["render_800x800_ms"] / render["frame_ms"]
+            except Exception as err:  # the comparator must never take the bench line down with it
+                ref_gpu = {"unavailable": f"{type(err).__name__}: {err}"[:300]}
         step_flop = n_rays * (SC + SC + SF) * FLOP_TRAIN_PER_EVAL
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": "single training step (coarse 64 + fine 64+128, fwd+bwd, Adam), 4096-ray batch per GPU, "
+            "config": {"workload": f"single training step (coarse 64 + fine 64+128, fwd+bwd, Adam), {n_rays}-ray batch per GPU, "
                                    "lego-shaped synthetic scene, 800x800 cameras, near/far 2/6",
                        "rays_per_gpu": n_rays, "global_rays": n_rays * world, "samples": [SC, SF],
                        "l2_policy": "per-step working set (activation cache + gradients, >1 GB) exceeds the 126 MB L2",
@@ -468,7 +628,8 @@ def run_b200(args):
                     "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks,
             "step_tensor_frac_sustained": step_flop / (ms_dev / args.steps * 1e-3) / 1e12 / pk["tf_sustained"],
-            "roofline": roof, "roofline_mlp": roof_mlp, "roofline_stages": stages, "cpu_baseline": cpu, "render": render,
+            "roofline": roof, "roofline_mlp": roof_mlp, "roofline_stages": stages, "cpu_baseline": cpu, "reference_gpu": ref_gpu,
+            "render": render,
             "loss_last": [float(x) for x in losses_host[total_steps - 1]],
         }
         print(json.dumps(line))
@@ -485,6 +646,8 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("NERF_B200_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--rays", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip the same-box torch-CUDA run of the unmodified reference")
+    ap.add_argument("--quick", action="store_true", help="shorter reference legs")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel of the iteration instead of replaying the captured CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -27,8 +27,8 @@ def tn():
     return mod
 
 
-def header_symbols():
-    text = open(os.path.join(ROOT, "include", "nerf_b200.h")).read()
+def header_symbols(name="nerf_b200.h"):
+    text = open(os.path.join(ROOT, "include", name)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(nerf_[a-z0-9_]+)\s*\(", text)))
 
@@ -41,6 +41,19 @@ def test_library_exports_every_declared_symbol(tn):
         assert hasattr(lib, s), f"{s} declared in include/nerf_b200.h but not exported"
     assert set(tn._lib.EXPORTED_SYMBOLS) == set(syms), "ctypes prototypes out of sync with the header"
     assert tn._lib.load().nerf_version() >= 100
+
+
+def test_debug_header_symbols_live_in_their_libraries(tn):
+    """include/nerf_b200_debug.h: the timeline hooks are exported by the main library, the tcgen05 self tests and
+    micro-benchmarks only by libnerf_b200_selftest.so (they are not part of the product library)."""
+    syms = set(header_symbols("nerf_b200_debug.h"))
+    assert syms == set(tn._lib.DEBUG_SYMBOLS) | set(tn._lib.SELFTEST_SYMBOLS)
+    main = ctypes.CDLL(tn._lib.LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+    st = tn._lib.load_selftest()
+    for s in tn._lib.DEBUG_SYMBOLS:
+        assert hasattr(main, s)
+    for s in tn._lib.SELFTEST_SYMBOLS:
+        assert hasattr(st, s) and not hasattr(main, s), s
 
 
 def test_struct_layouts_match_header(tn):

@@ -22,7 +22,7 @@ def tn():
 def _umma(tn, a_bits, b_bits, n, k, variant):
     lib = tn._lib.load()
     d = torch.empty((128, n), device="cuda", dtype=torch.float32)
-    rc = lib.nerf_selftest_umma(tn._lib.c_void_p(a_bits.data_ptr()), tn._lib.c_void_p(b_bits.data_ptr()),
+    rc = tn._lib.load_selftest().nerf_selftest_umma(tn._lib.c_void_p(a_bits.data_ptr()), tn._lib.c_void_p(b_bits.data_ptr()),
                                 tn._lib.c_void_p(d.data_ptr()), n, k, variant, tn._lib.stream())
     tn._lib.check(rc, "nerf_selftest_umma")
     torch.cuda.synchronize()
@@ -150,7 +150,7 @@ def test_umma_cta_pair(tn, n, k, ts):
     b = torch.randn(n, k, device="cuda").bfloat16()
     d = torch.zeros(256, n, device="cuda")
     vp = tn._lib.c_void_p
-    tn._lib.check(lib.nerf_selftest_umma2(vp(a.data_ptr()), vp(b.data_ptr()), tn._lib.ptr(d), n, k, ts, 1, 0, None,
+    tn._lib.check(tn._lib.load_selftest().nerf_selftest_umma2(vp(a.data_ptr()), vp(b.data_ptr()), tn._lib.ptr(d), n, k, ts, 1, 0, None,
                                           tn._lib.stream()), "umma2")
     torch.cuda.synchronize()
     torch.testing.assert_close(d, a.float() @ b.float().t(), rtol=1e-4, atol=1e-3)

@@ -9,7 +9,7 @@ P, VP = tn._lib.ptr, tn._lib.c_void_p
 out = torch.zeros(2 * 148, dtype=torch.int64, device="cuda")
 def rate(blocks, iters, n, mode, bg_warps=0, bg_iters=0, bg_store=0):
     out.zero_()
-    tn._lib.check(lib.nerf_selftest_mma_rate(blocks, iters, n, mode, bg_warps, bg_iters, bg_store, VP(out.data_ptr()), tn._lib.stream()), "rate")
+    tn._lib.check(tn._lib.load_selftest().nerf_selftest_mma_rate(blocks, iters, n, mode, bg_warps, bg_iters, bg_store, VP(out.data_ptr()), tn._lib.stream()), "rate")
     torch.cuda.synchronize()
     mma = out[:blocks].float().mean().item() / max(1, iters * 4)
     bg = out[blocks:2 * blocks].float().mean().item() / max(1, bg_iters)

@@ -29,9 +29,8 @@ def fwd(c):
     tn._lib.check(lib.nerf_mlp_bf16_forward(P(packed, torch.uint8), None, None, P(ray_o), P(ray_d), P(t), s, m, P(sig), P(rgb),
                                             P(c, torch.uint8) if c is not None else None, tn._lib.stream()), "fwd")
 def bwd(mask):
-    lib.nerf_debug_set_bwd_phases(mask)
-    tn._lib.check(lib.nerf_mlp_bf16_backward(P(packed, torch.uint8), P(cache, torch.uint8), P(rgb), m, P(g_sig), P(g_rgb), garr,
-                                             P(scratch, torch.uint8), tn._lib.stream()), "bwd")
+    tn._lib.check(lib.nerf_mlp_bf16_backward_part(P(packed, torch.uint8), P(cache, torch.uint8), P(rgb), m, P(g_sig), P(g_rgb), garr,
+                                                  P(scratch, torch.uint8), mask, 0, (m + 127) // 128, 0, tn._lib.stream()), "bwd")
 cases = [("mlp_fwd inference", lambda: fwd(None)), ("mlp_fwd training", lambda: fwd(cache)), ("mlp_dgrad", lambda: bwd(2)),
          ("mlp_wgrad", lambda: bwd(4))]
 fwd(cache); bwd(7); torch.cuda.synchronize()
@@ -54,4 +53,3 @@ for name, fn in cases:
     us = e0.elapsed_time(e1) * 1e3 / reps
     clk = np.array([c for c, _ in samples[len(samples) // 4:]]); pw = np.array([p for _, p in samples[len(samples) // 4:]])
     print(f"{name:20s} {us:8.1f} us/launch sustained | SM clock median {np.median(clk):6.0f} min {clk.min():6.0f} MHz | power median {np.median(pw):6.0f} W max {pw.max():6.0f} W")
-lib.nerf_debug_set_bwd_phases(7)

@@ -12,7 +12,7 @@ for trial in range(300):
     n, k = (128, 256) if trial % 2 == 0 else (256, 256)
     a = torch.randn(128, k, device="cuda").bfloat16(); b = torch.randn(n, k, device="cuda").bfloat16()
     d = torch.zeros(128, n, device="cuda")
-    tn._lib.check(lib.nerf_selftest_umma(VP(a.data_ptr()), VP(b.data_ptr()), P(d), n, k, 3, tn._lib.stream()), "umma split")
+    tn._lib.check(tn._lib.load_selftest().nerf_selftest_umma(VP(a.data_ptr()), VP(b.data_ptr()), P(d), n, k, 3, tn._lib.stream()), "umma split")
     torch.cuda.synchronize()
     ref = a.float() @ b.float().T
     err = (d - ref).abs().max().item()
@@ -27,7 +27,7 @@ for trial in range(100):
     n, k, reps = 256, 256, 64
     a = torch.randint(-1, 2, (128, k), device="cuda").bfloat16(); b = torch.randint(-1, 2, (n, k), device="cuda").bfloat16()
     d = torch.zeros(128, n, device="cuda")
-    tn._lib.check(lib.nerf_selftest_umma(VP(a.data_ptr()), VP(b.data_ptr()), P(d), n, k, 3 + 16 * (reps - 1), tn._lib.stream()), "umma split")
+    tn._lib.check(tn._lib.load_selftest().nerf_selftest_umma(VP(a.data_ptr()), VP(b.data_ptr()), P(d), n, k, 3 + 16 * (reps - 1), tn._lib.stream()), "umma split")
     torch.cuda.synchronize()
     ref = (a.float() @ b.float().T) * reps
     mism += int((d != ref).sum().item())

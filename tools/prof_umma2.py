@@ -11,7 +11,7 @@ for ts in (0, 1):
         for k in (64, 256):
             a = torch.randn(256, k, device="cuda").bfloat16(); b = torch.randn(n, k, device="cuda").bfloat16()
             d = torch.zeros(256, n, device="cuda")
-            tn._lib.check(lib.nerf_selftest_umma2(VP(a.data_ptr()), VP(b.data_ptr()), P(d), n, k, ts, 1, 0, None, tn._lib.stream()), "umma2")
+            tn._lib.check(tn._lib.load_selftest().nerf_selftest_umma2(VP(a.data_ptr()), VP(b.data_ptr()), P(d), n, k, ts, 1, 0, None, tn._lib.stream()), "umma2")
             torch.cuda.synchronize()
             ref = a.float() @ b.float().T
             err = (d - ref).abs().max().item()
@@ -23,7 +23,7 @@ for ts in (0, 1):
         a = torch.randn(256, k, device="cuda").bfloat16(); b = torch.randn(n, k, device="cuda").bfloat16()
         d = torch.zeros(256, n, device="cuda")
         iters = 500
-        tn._lib.check(lib.nerf_selftest_umma2(VP(a.data_ptr()), VP(b.data_ptr()), P(d), n, k, ts, 74, iters, VP(cyc.data_ptr()), tn._lib.stream()), "umma2")
+        tn._lib.check(tn._lib.load_selftest().nerf_selftest_umma2(VP(a.data_ptr()), VP(b.data_ptr()), P(d), n, k, ts, 74, iters, VP(cyc.data_ptr()), tn._lib.stream()), "umma2")
         torch.cuda.synchronize()
         per = cyc.float().mean().item() / (iters * k / 16)
         print(f"rate {'TS' if ts else 'SS'} pair M=256 N={n}: {per:6.1f} cycles per MMA (tensor floor {n / 2:.0f}; single-CTA M=128 measured: TS 93/137, SS 104/168)")
@@ -37,7 +37,7 @@ for ts in (0, 1):
         a = torch.randn(256, k, device="cuda").bfloat16(); b = torch.randn(n, k, device="cuda").bfloat16()
         d = torch.zeros(256, n, device="cuda")
         iters = 500
-        tn._lib.check(lib.nerf_selftest_umma2(VP(a.data_ptr()), VP(b.data_ptr()), P(d), n, k, ts | 2, 74, iters, VP(cyc2.data_ptr()), tn._lib.stream()), "umma2 both")
+        tn._lib.check(tn._lib.load_selftest().nerf_selftest_umma2(VP(a.data_ptr()), VP(b.data_ptr()), P(d), n, k, ts | 2, 74, iters, VP(cyc2.data_ptr()), tn._lib.stream()), "umma2 both")
         torch.cuda.synchronize()
         err = (d - a.float() @ b.float().T).abs().max().item()
         per = cyc2.float().mean().item() / (2 * iters * k / 16)

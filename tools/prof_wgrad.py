@@ -19,12 +19,11 @@ tn._lib.check(lib.nerf_mlp_bf16_forward(P(packed, torch.uint8), None, None, P(ra
 g_sigma = torch.randn(m, device="cuda") * 1e-3; g_rgb = torch.randn(m, 3, device="cuda") * 1e-3
 grads = [torch.zeros_like(p) for p in net.parameters()]
 gp = tn._lib.pointer_array(grads)
-def bwd():
-    tn._lib.check(lib.nerf_mlp_bf16_backward(P(packed, torch.uint8), P(cache, torch.uint8), P(rgb), m, P(g_sigma), P(g_rgb), gp,
-                                             P(scratch, torch.uint8), tn._lib.stream()), "bwd")
-bwd(); torch.cuda.synchronize()
+def bwd(mask=4):
+    tn._lib.check(lib.nerf_mlp_bf16_backward_part(P(packed, torch.uint8), P(cache, torch.uint8), P(rgb), m, P(g_sigma), P(g_rgb), gp,
+                                                  P(scratch, torch.uint8), mask, 0, (m + 127) // 128, 0, tn._lib.stream()), "bwd")
+bwd(7); torch.cuda.synchronize()
 prof = torch.zeros(148 * 16, dtype=torch.int64, device="cuda")
-lib.nerf_debug_set_bwd_phases(4)
 lib.nerf_debug_set_wgrad_profile(VP(prof.data_ptr()))
 bwd(); torch.cuda.synchronize()
 lib.nerf_debug_set_wgrad_profile(None)
@@ -38,4 +37,4 @@ ev0.record()
 for _ in range(5): bwd()
 ev1.record(); torch.cuda.synchronize()
 print(f"wgrad alone: {ev0.elapsed_time(ev1)/5*1e3:.0f} us")
-lib.nerf_debug_set_bwd_phases(7)
+

@@ -10,7 +10,7 @@ x = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
 names = {0: "st.global.v4", 1: "st.global.cs.v4", 2: "bulk store", 3: "bulk store evict_first", 4: "bulk store evict_last"}
 for blocks in (148, 296, 592):
     for mode in range(5):
-        def run(): tn._lib.check(lib.nerf_selftest_write_bw(VP(x.data_ptr()), nbytes, mode, blocks, tn._lib.stream()), "wbw")
+        def run(): tn._lib.check(tn._lib.load_selftest().nerf_selftest_write_bw(VP(x.data_ptr()), nbytes, mode, blocks, tn._lib.stream()), "wbw")
         run(); torch.cuda.synchronize()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()

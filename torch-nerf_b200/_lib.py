@@ -14,6 +14,7 @@ import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libnerf_b200.so")
+SELFTEST_LIB_PATH = os.path.join(_PKG, "lib", "libnerf_b200_selftest.so")
 
 NERF_OK, NERF_ERR_ARG, NERF_ERR_CUDA = 0, 1, 2
 NUM_PARAM_TENSORS = 22
@@ -65,18 +66,27 @@ _PROTOTYPES = {
     "nerf_mlp_bf16_forward": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int64, _P, _P, _P, _P]),
     "nerf_mlp_bf16_bwd_scratch_bytes": (c_size_t, [c_int64]),
     "nerf_mlp_bf16_backward": (c_int, [_P, _P, _P, c_int64, _P, _P, POINTER(_P), _P, _P]),
-    "nerf_selftest_umma": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
+    "nerf_mlp_bf16_backward_part": (c_int, [_P, _P, _P, c_int64, _P, _P, POINTER(_P), _P, c_int, c_int64, c_int64, c_int, _P]),
+}
+# include/nerf_b200_debug.h: timeline hooks of the main library ...
+_DEBUG_PROTOTYPES = {
     "nerf_debug_set_profile_buffer": (c_int, [_P, c_int]),
-    "nerf_debug_set_bwd_phases": (c_int, [c_int]),
     "nerf_debug_set_wgrad_profile": (c_int, [_P]),
+}
+# ... and the building-block self tests / micro-benchmarks of libnerf_b200_selftest.so (tests/ and tools/ only)
+_SELFTEST_PROTOTYPES = {
+    "nerf_selftest_umma": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
     "nerf_selftest_mma_rate": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "nerf_selftest_umma2": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "nerf_selftest_write_bw": (c_int, [_P, c_size_t, c_int, c_int, _P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
+DEBUG_SYMBOLS = tuple(_DEBUG_PROTOTYPES)
+SELFTEST_SYMBOLS = tuple(_SELFTEST_PROTOTYPES)
 
 _lib = None
+_selftest_lib = None
 
 
 def load() -> ctypes.CDLL:
@@ -88,13 +98,29 @@ def load() -> ctypes.CDLL:
                 f"{LIB_PATH} is missing: build it with `python torch-nerf_b200/build.py` "
                 "(there is no CPU or PyTorch fallback for the B200 path)"
             )
-        lib = ctypes.CDLL(LIB_PATH)
-        for name, (res, args) in _PROTOTYPES.items():
+        lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+        for name, (res, args) in {**_PROTOTYPES, **_DEBUG_PROTOTYPES}.items():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
         _lib = lib
     return _lib
+
+
+def load_selftest() -> ctypes.CDLL:
+    """libnerf_b200_selftest.so: the tcgen05 building-block checks and micro-benchmarks (tests/ and tools/ only)."""
+    global _selftest_lib
+    if _selftest_lib is None:
+        load()
+        if not os.path.exists(SELFTEST_LIB_PATH):
+            raise RuntimeError(f"{SELFTEST_LIB_PATH} is missing: build it with `python torch-nerf_b200/build.py`")
+        lib = ctypes.CDLL(SELFTEST_LIB_PATH)
+        for name, (res, args) in _SELFTEST_PROTOTYPES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _selftest_lib = lib
+    return _selftest_lib
 
 
 def last_error() -> str:

@@ -15,17 +15,16 @@ void set_error(const char* fmt, ...) {
 }
 
 int sm_count() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) {
-      cached = n;
-    } else {
-      return 148;
-    }
-  }
-  return cached;
+  // cached per device: a process may drive several GPUs (the value is written once per device and is idempotent,
+  // so concurrent first calls are harmless)
+  constexpr int kMaxDev = 64;
+  static int cached[kMaxDev] = {};
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev >= 0 && dev < kMaxDev && cached[dev] > 0) return cached[dev];
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+  if (dev >= 0 && dev < kMaxDev) cached[dev] = n;
+  return n;
 }
 
 }  // namespace nerf

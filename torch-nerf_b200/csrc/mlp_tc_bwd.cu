@@ -52,6 +52,7 @@ struct DgradArgs {
   const float* g_rgb;     // (M,3)
   uint8_t* scratch;       // gradient tile images + gz + g_sigma_pre
   int64_t m;
+  int64_t tile0, tile1;   // this launch covers tiles [tile0, tile1) of the m rows (tile0 even)
 };
 
 // `neg` holds the sign bits of the forward pre-activations, column i at bit (31 - i): set = ReLU was inactive
@@ -95,8 +96,8 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t ntiles = num_tiles(a.m);
-  const int64_t npairs = (ntiles + 1) / 2;
+  const int64_t ntiles = a.tile1;
+  const int64_t pair0 = a.tile0 / 2, npairs = (a.tile1 + 1) / 2;
   {
     const float* cgp = reinterpret_cast<const float*>(a.packed + kPackedConstOff);
     for (int i = threadIdx.x; i < 640; i += kDgThreads) sC[i] = __ldg(cgp + kCW8Row0 + i);  // w8row0 then wout (contiguous)
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
   if (warp == 0) {
     const bool leader = elect_one();
     uint32_t g = 0;
-    for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+    for (int64_t pair = pair0 + blockIdx.x; pair < npairs; pair += gridDim.x) {
       const uint8_t* src = a.packed + kPackedBwdOff;
       for (int c = 0; c < kBwdChunks; ++c) {
         const uint32_t s = g % kDgStages, ph = (g / kDgStages) & 1;
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
     const uint32_t sW_u = smem_u32(sW);
     const uint32_t acc = tmem_base + (uint32_t)slot * kDgTmSlot;
     const uint32_t a_tm = acc + kDgTmA;
-    for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+    for (int64_t pair = pair0 + blockIdx.x; pair < npairs; pair += gridDim.x) {
       for (int j = 0; j < kNumBwdLayers; ++j) {
         const int nk = bwd_nk(j);
         for (int h = 0; h < 2; ++h) {
@@ -228,9 +229,9 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
         }
       }
     };
-    load_heads(2 * (int64_t)blockIdx.x + slot);
+    load_heads(2 * (pair0 + (int64_t)blockIdx.x) + slot);
 
-    for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+    for (int64_t pair = pair0 + blockIdx.x; pair < npairs; pair += gridDim.x) {
       const int64_t tile = 2 * pair + slot;
       const bool valid = tile < ntiles;
       uint8_t* g_tile = a.scratch + (size_t)tile * kGradTileBytes;
@@ -389,6 +390,7 @@ struct WgradArgs {
   const uint8_t* scratch;
   ParamPtrs grads;
   int64_t m;
+  int64_t tile0, tile1;      // this launch covers tiles [tile0, tile1) of the m rows
   unsigned long long* prof;  // optional per-CTA timeline (nerf_debug_set_wgrad_profile): 8 values per CTA
 };
 
@@ -406,7 +408,7 @@ struct Segment {
 // cost-balanced contiguous partition of (unit, tile) pairs over the grid
 __device__ __forceinline__ int unit_cost(int u) { return c_wunits[u].cost; }
 
-__device__ inline int build_segments(int64_t ntiles, Segment* seg) {
+__device__ inline int build_segments(int64_t tile_first, int64_t ntiles, Segment* seg) {
   int64_t total = 0;
   for (int u = 0; u < kNumWUnits; ++u) total += ntiles * unit_cost(u);
   const int64_t lo = total * blockIdx.x / gridDim.x, hi = total * (blockIdx.x + 1) / gridDim.x;
@@ -422,8 +424,8 @@ __device__ inline int build_segments(int64_t ntiles, Segment* seg) {
       const int64_t t0 = (a + c - 1) / c, t1 = (b + c - 1) / c;
       if (t1 > t0) {
         seg[n].unit = u;
-        seg[n].tile0 = t0;
-        seg[n].tile1 = t1 < ntiles ? t1 : ntiles;
+        seg[n].tile0 = tile_first + t0;
+        seg[n].tile1 = tile_first + (t1 < ntiles ? t1 : ntiles);
         ++n;
       }
     }
@@ -505,7 +507,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
   __shared__ uint32_t stage_base[kWgMaxStages];  // completed phases of every stage's barriers (segments change the ring geometry)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t ntiles = num_tiles(a.m);
+  const int64_t ntiles = a.tile1 - a.tile0;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kWgMaxStages; ++i) {
       mbar_init(&full[i], 1);
@@ -514,7 +516,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
     mbar_init(acc_done, 1);
     fence_barrier_init();
     for (int i = 0; i < kWgMaxStages; ++i) stage_base[i] = 0;
-    nseg_s = build_segments(ntiles, segs);
+    nseg_s = build_segments(a.tile0, ntiles, segs);
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -775,9 +777,68 @@ __global__ void zero_grads_kernel(ParamPtrs g) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0.f;
 }
 
-static bool g_wunits_ready = false;
 static unsigned long long* g_wgrad_prof = nullptr;
-static int g_bwd_phase_mask = 7;  // bit 0: zero the gradients, bit 1: dgrad chain, bit 2: wgrad (profiling aid)
+
+// Per-device one-time setup (shared-memory opt-in of the kernels, the wgrad unit table in constant memory).  A process
+// that drives several GPUs must do this on each of them, hence the per-device flags.
+constexpr int kMaxDevices = 64;
+static bool g_bwd_ready[kMaxDevices] = {};
+
+static int bwd_device_setup() {
+  int dev = 0;
+  NERF_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < kMaxDevices && g_bwd_ready[dev]) return NERF_OK;
+  NERF_CUDA(cudaFuncSetAttribute(mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDgSmemBytes));
+  NERF_CUDA(cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
+  WUnit table[kNumWUnits];
+  build_wunits(table);
+  NERF_CUDA(cudaMemcpyToSymbol(c_wunits, table, sizeof(table)));
+  if (dev >= 0 && dev < kMaxDevices) g_bwd_ready[dev] = true;
+  return NERF_OK;
+}
+
+// phases: bit 0 zero the gradients, bit 1 dgrad chain, bit 2 wgrad; tiles [tile0, tile1); ctas = grid size (0 = one per SM)
+static int launch_backward(const void* packed_dev, const void* cache_dev, const float* rgb_dev, int64_t m,
+                           const float* g_sigma_dev, const float* g_rgb_dev, float* const* grads, void* scratch_dev,
+                           int phases, int64_t tile0, int64_t tile1, int ctas, cudaStream_t st) {
+  if (int rc = bwd_device_setup()) return rc;
+  ParamPtrs gp;
+  for (int i = 0; i < NERF_NUM_PARAM_TENSORS; ++i) {
+    NERF_CHECK_ARG(grads[i] != nullptr, "nerf_mlp_bf16_backward: null gradient pointer");
+    gp.p[i] = grads[i];
+  }
+  if (phases & 1) {
+    zero_grads_kernel<<<dim3(32, 22), 256, 0, st>>>(gp);
+    NERF_LAUNCH_CHECK();
+  }
+  const int sms = (ctas > 0 && ctas < sm_count()) ? ctas : sm_count();
+  if (tile1 <= tile0) return NERF_OK;
+  if (phases & 2) {
+    DgradArgs a;
+    a.packed = reinterpret_cast<const uint8_t*>(packed_dev);
+    a.cache = reinterpret_cast<const uint8_t*>(cache_dev);
+    a.rgb = rgb_dev, a.g_sigma = g_sigma_dev, a.g_rgb = g_rgb_dev;
+    a.scratch = reinterpret_cast<uint8_t*>(scratch_dev);
+    a.m = m;
+    a.tile0 = tile0, a.tile1 = tile1;
+    const int64_t npairs = (tile1 + 1) / 2 - tile0 / 2;  // a CTA works on two tiles at a time
+    const int grid = (int)(npairs < sms ? npairs : sms);
+    mlp_dgrad_kernel<<<grid, kDgThreads, kDgSmemBytes, st>>>(a);
+    NERF_LAUNCH_CHECK();
+  }
+  if (phases & 4) {
+    WgradArgs a;
+    a.cache = reinterpret_cast<const uint8_t*>(cache_dev);
+    a.scratch = reinterpret_cast<const uint8_t*>(scratch_dev);
+    a.grads = gp;
+    a.m = m;
+    a.tile0 = tile0, a.tile1 = tile1;
+    a.prof = g_wgrad_prof;
+    mlp_wgrad_kernel<<<sms, kWgThreads, kWgSmemBytes, st>>>(a);
+    NERF_LAUNCH_CHECK();
+  }
+  return NERF_OK;
+}
 
 }  // namespace nerf
 
@@ -788,62 +849,27 @@ extern "C" int nerf_debug_set_wgrad_profile(unsigned long long* buf_dev) {
   return NERF_OK;
 }
 
-extern "C" int nerf_debug_set_bwd_phases(int mask) {
-  g_bwd_phase_mask = mask;
-  return NERF_OK;
-}
-
 extern "C" int nerf_mlp_bf16_backward(const void* packed_dev, const void* cache_dev, const float* rgb_dev, int64_t m,
                                       const float* g_sigma_dev, const float* g_rgb_dev, float* const* grads,
                                       void* scratch_dev, nerf_stream_t stream) {
   NERF_CHECK_ARG(m > 0, "nerf_mlp_bf16_backward: row count must be positive");
   NERF_CHECK_ARG(packed_dev && cache_dev && rgb_dev && g_sigma_dev && g_rgb_dev && grads && scratch_dev,
                  "nerf_mlp_bf16_backward: null pointer");
-  cudaStream_t st = as_stream(stream);
-  static bool attr_set = false;
-  if (!attr_set) {
-    NERF_CUDA(cudaFuncSetAttribute(mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDgSmemBytes));
-    NERF_CUDA(cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
-    attr_set = true;
-  }
-  if (!g_wunits_ready) {
-    WUnit table[kNumWUnits];
-    build_wunits(table);
-    NERF_CUDA(cudaMemcpyToSymbol(c_wunits, table, sizeof(table)));
-    g_wunits_ready = true;
-  }
-  ParamPtrs gp;
-  for (int i = 0; i < NERF_NUM_PARAM_TENSORS; ++i) {
-    NERF_CHECK_ARG(grads[i] != nullptr, "nerf_mlp_bf16_backward: null gradient pointer");
-    gp.p[i] = grads[i];
-  }
-  if (g_bwd_phase_mask & 1) {
-    zero_grads_kernel<<<dim3(32, 22), 256, 0, st>>>(gp);
-    NERF_LAUNCH_CHECK();
-  }
-  const int64_t ntiles = num_tiles(m);
-  const int sms = sm_count();
-  if (g_bwd_phase_mask & 2) {
-    DgradArgs a;
-    a.packed = reinterpret_cast<const uint8_t*>(packed_dev);
-    a.cache = reinterpret_cast<const uint8_t*>(cache_dev);
-    a.rgb = rgb_dev, a.g_sigma = g_sigma_dev, a.g_rgb = g_rgb_dev;
-    a.scratch = reinterpret_cast<uint8_t*>(scratch_dev);
-    a.m = m;
-    const int64_t npairs = (ntiles + 1) / 2;  // a CTA works on two tiles at a time
-    const int grid = (int)(npairs < sms ? npairs : sms);
-    mlp_dgrad_kernel<<<grid, kDgThreads, kDgSmemBytes, st>>>(a);
-    NERF_LAUNCH_CHECK();
-  }
-  if (g_bwd_phase_mask & 4) {
-    WgradArgs a;
-    a.cache = reinterpret_cast<const uint8_t*>(cache_dev);
-    a.scratch = reinterpret_cast<const uint8_t*>(scratch_dev);
-    a.grads = gp;
-    a.m = m;
-    a.prof = g_wgrad_prof;
-    mlp_wgrad_kernel<<<sms, kWgThreads, kWgSmemBytes, st>>>(a);
-    NERF_LAUNCH_CHECK();
-  }
-  return NERF_OK;
+  return launch_backward(packed_dev, cache_dev, rgb_dev, m, g_sigma_dev, g_rgb_dev, grads, scratch_dev, 7, 0, num_tiles(m), 0,
+                         as_stream(stream));
+}
+
+extern "C" int nerf_mlp_bf16_backward_part(const void* packed_dev, const void* cache_dev, const float* rgb_dev, int64_t m,
+                                           const float* g_sigma_dev, const float* g_rgb_dev, float* const* grads,
+                                           void* scratch_dev, int phases, int64_t tile0, int64_t tile1, int ctas,
+                                           nerf_stream_t stream) {
+  NERF_CHECK_ARG(m > 0, "nerf_mlp_bf16_backward_part: row count must be positive");
+  NERF_CHECK_ARG(packed_dev && cache_dev && rgb_dev && g_sigma_dev && g_rgb_dev && grads && scratch_dev,
+                 "nerf_mlp_bf16_backward_part: null pointer");
+  NERF_CHECK_ARG((phases & ~7) == 0, "nerf_mlp_bf16_backward_part: phases is a mask of bits 0..2");
+  NERF_CHECK_ARG(tile0 >= 0 && (tile0 & 1) == 0 && tile1 <= num_tiles(m) && tile0 <= tile1,
+                 "nerf_mlp_bf16_backward_part: need 0 <= tile0 <= tile1 <= tiles(m) with tile0 even");
+  NERF_CHECK_ARG(ctas >= 0, "nerf_mlp_bf16_backward_part: negative CTA count");
+  return launch_backward(packed_dev, cache_dev, rgb_dev, m, g_sigma_dev, g_rgb_dev, grads, scratch_dev, phases, tile0, tile1,
+                         ctas, as_stream(stream));
 }

@@ -613,11 +613,16 @@ extern "C" int nerf_mlp_bf16_forward(const void* packed_dev, const float* pts_de
   NERF_CHECK_ARG(packed_dev && sigma_dev && rgb_dev, "nerf_mlp_bf16_forward: null pointer");
   NERF_CHECK_ARG((pts_dev && dirs_dev) || (ray_o_dev && ray_d_dev && t_dev && s > 0),
                  "nerf_mlp_bf16_forward: give (pts, dirs) or (ray_o, ray_d, t, s)");
-  static bool attr_set = false;
-  if (!attr_set) {
-    NERF_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
-    NERF_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
-    attr_set = true;
+  {  // the shared-memory opt-in is a per-device function attribute
+    constexpr int kMaxDevices = 64;
+    static bool attr_set[kMaxDevices] = {};
+    int dev = 0;
+    NERF_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices || !attr_set[dev]) {
+      NERF_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
+      NERF_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
+      if (dev >= 0 && dev < kMaxDevices) attr_set[dev] = true;
+    }
   }
   FwdArgs a;
   a.packed = reinterpret_cast<const uint8_t*>(packed_dev);

@@ -100,7 +100,9 @@ static int build_pack_table(PackChunk* t) {
   return n;
 }
 
-static bool g_pack_table_ready = false;
+// the chunk table lives in constant memory, i.e. per device: uploaded once on every device the process uses
+constexpr int kMaxDevices = 64;
+static bool g_pack_table_ready[kMaxDevices] = {};
 static int g_pack_chunks = 0;
 
 }  // namespace nerf
@@ -114,11 +116,13 @@ size_t nerf_mlp_bf16_packed_bytes(void) { return kPackedBytes; }
 int nerf_mlp_bf16_pack(const float* const* params, void* packed_dev, nerf_stream_t stream) {
   NERF_CHECK_ARG(params && packed_dev, "nerf_mlp_bf16_pack: null pointer");
   cudaStream_t st = as_stream(stream);
-  if (!g_pack_table_ready) {
+  int dev = 0;
+  NERF_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices || !g_pack_table_ready[dev]) {
     PackChunk table[kMaxPackChunks];
     g_pack_chunks = build_pack_table(table);
     NERF_CUDA(cudaMemcpyToSymbol(c_pack, table, sizeof(PackChunk) * g_pack_chunks));
-    g_pack_table_ready = true;
+    if (dev >= 0 && dev < kMaxDevices) g_pack_table_ready[dev] = true;
   }
   ParamPtrs pp;
   for (int i = 0; i < NERF_NUM_PARAM_TENSORS; ++i) {
