@@ -322,6 +322,86 @@ def reference_gpu_block(dev, n_rays):
     return out
 
 
+def dropin_block(tn, dev, n_rays, eng_render):
+    """The same workloads through the reference-facing plugin API of this package -- VolumeRenderer.render_scene with
+    StratifiedSampler / QuadratureIntegrator / PrimitiveCube(NeRF) and torch autograd + torch.optim.Adam, driven exactly
+    like train.py:130-218 and render.py:58-107 -- instead of the fused engine: what a maintainer gets by swapping the
+    classes in runner_utils.py and nothing else ((N,S,3) sample points are materialised here, as the API demands)."""
+    import torch
+
+    out = {}
+    intr, c2w = _ref_scene(IMG)
+    for precision in ("bf16", "fp32"):
+        torch.manual_seed(0)
+        nets = [tn.NeRF(63, 27, precision=precision).to(dev) for _ in range(2)]
+        enc = {"coord_enc": tn.PositionalEncoder(3, 10, True), "dir_enc": tn.PositionalEncoder(3, 4, True)}
+        scenes = [tn.PrimitiveCube(net, enc) for net in nets]
+        cam = tn.PerspectiveCamera(intr, c2w, 2.0, 6.0)
+        ren = tn.VolumeRenderer(tn.QuadratureIntegrator(), tn.StratifiedSampler(), cam)
+        opt = torch.optim.Adam([p for net in nets for p in net.parameters()], lr=5e-4, eps=1e-8)
+        sched = torch.optim.lr_scheduler.ExponentialLR(opt, (5e-5 / 5e-4) ** (1.0 / 300000))
+        loss_fn = torch.nn.MSELoss()
+        gt = torch.rand(IMG * IMG, 3)
+        dev_i = dev.index if dev.index is not None else torch.cuda.current_device()
+
+        def step():
+            opt.zero_grad()
+            ren.camera = tn.PerspectiveCamera(intr, c2w, 2.0, 6.0)
+            pred_c, idx, w_c = ren.render_scene(scenes[0], n_rays, SC, False, dev_i)
+            loss = loss_fn(gt[idx].to(dev), pred_c)
+            pred_f, idx_f, _ = ren.render_scene(scenes[1], n_rays, (SC, SF), False, dev_i, pixel_indices=idx, weights=w_c)
+            loss = loss + loss_fn(gt[idx_f].to(dev), pred_f)
+            loss.backward()
+            opt.step()
+            sched.step()
+
+        steps = 10 if precision == "bf16" else 3
+        for _ in range(3 if precision == "bf16" else 1):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[f"train_{precision}"] = {"rays_per_step": n_rays, "ms_per_step": ms, "rays_per_s": n_rays / (ms * 1e-3), "steps": steps}
+        # config C1: 100x100 frame, num_ray_batch = 10000 // 4096 = 2 (render.py:81-99)
+        intr1, c2w1 = _ref_scene(100)
+        ren.camera = tn.PerspectiveCamera(intr1, c2w1, 2.0, 6.0)
+
+        def frame():
+            with torch.no_grad():
+                img, idx, wts = ren.render_scene(scenes[0], 10000, SC, False, dev_i, num_ray_batch=2)
+                img, _, _ = ren.render_scene(scenes[1], 10000, (SC, SF), False, dev_i, pixel_indices=idx, weights=wts, num_ray_batch=2)
+            return img.clamp(0.0, 1.0)
+
+        frame()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            frame()
+        e1.record()
+        torch.cuda.synchronize()
+        out[f"c1_render_100x100_{precision}_ms"] = e0.elapsed_time(e1) / 5
+        del nets, scenes, opt
+        torch.cuda.empty_cache()
+    # the fused engine on config C1 for comparison
+    intr1, c2w1 = _ref_scene(100)
+    cam1 = tn.PerspectiveCamera(intr1, c2w1, 2.0, 6.0)
+    eng_render.render_frame(cam1)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        eng_render.render_frame(cam1)
+    e1.record()
+    torch.cuda.synchronize()
+    out["c1_render_100x100_engine_bf16_ms"] = e0.elapsed_time(e1) / 5
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ B200 arm
 def run_b200(args):
     import torch
@@ -614,6 +694,12 @@ def run_b200(args):
                     ref_gpu["speedup_render_800x800"] = ref_gpu["render_800x800_ms"] / render["frame_ms"]
             except Exception as err:  # the comparator must never take the bench line down with it
                 ref_gpu = {"unavailable": f"{type(err).__name__}: {err}"[:300]}
+        dropin = None
+        if world == 1 and args.precision == "bf16" and not args.no_dropin:
+            try:
+                dropin = dropin_block(tn, dev, n_rays, eng_render)
+            except Exception as err:
+                dropin = {"unavailable": f"{type(err).__name__}: {err}"[:300]}
         step_flop = n_rays * (SC + SC + SF) * FLOP_TRAIN_PER_EVAL
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -628,7 +714,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks,
             "step_tensor_frac_sustained": step_flop / (ms_dev / args.steps * 1e-3) / 1e12 / pk["tf_sustained"],
-            "roofline": roof, "roofline_mlp": roof_mlp, "roofline_stages": stages, "cpu_baseline": cpu, "reference_gpu": ref_gpu,
+            "roofline": roof, "roofline_mlp": roof_mlp, "roofline_stages": stages, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "dropin": dropin,
             "render": render,
             "loss_last": [float(x) for x in losses_host[total_steps - 1]],
         }
@@ -647,6 +733,7 @@ def main():
     ap.add_argument("--rays", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip the same-box torch-CUDA run of the unmodified reference")
+    ap.add_argument("--no-dropin", action="store_true", help="skip timing the reference-facing plugin API (VolumeRenderer.render_scene)")
     ap.add_argument("--quick", action="store_true", help="shorter reference legs")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel of the iteration instead of replaying the captured CUDA graph")
     args = ap.parse_args()

@@ -86,3 +86,48 @@ def test_two_rank_sharded_step_equals_single_process():
     single = _flat_grads(*_problem())
     scale = np.abs(single).max()
     np.testing.assert_allclose(dist_flat / scale, single / scale, rtol=0, atol=2e-5)
+
+
+def _sync_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch_nerf_b200.parallel as par
+
+    torch.set_num_threads(1)
+    par.init_distributed("gloo")
+    torch.manual_seed(100 + rank)  # ranks seeded DIFFERENTLY on purpose
+    flat = torch.nn.Parameter(torch.randn(1000))
+    opt = torch.optim.Adam([flat], lr=5e-4 * (rank + 1), eps=1e-8)
+    sched = torch.optim.lr_scheduler.ExponentialLR(opt, 0.999)
+    if rank == 0:  # only rank 0 has taken steps (e.g. it alone found the checkpoint)
+        for _ in range(3):
+            flat.grad = torch.randn(1000)
+            opt.step()
+            sched.step()
+    par.broadcast_replica_state(flat, opt, sched)
+    st = opt.state[flat]
+    ret[rank] = (flat.detach().numpy().copy(), float(st["step"]), st["exp_avg"].numpy().copy(), st["exp_avg_sq"].numpy().copy(),
+                 opt.param_groups[0]["lr"], sched.last_epoch)
+    # one more identical step on both ranks must keep them identical
+    flat.grad = torch.full((1000,), 0.25)
+    opt.step()
+    sched.step()
+    ret[f"after{rank}"] = (flat.detach().numpy().copy(), opt.param_groups[0]["lr"])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_replica_state_broadcast_makes_differently_seeded_ranks_identical():
+    """Trainer(world > 1) must not depend on the caller seeding every rank identically."""
+    sys.path.insert(0, ROOT)
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_sync_worker, args=(world, port, ret), nprocs=world, join=True)
+        r0, r1 = ret[0], ret[1]
+        a0, a1 = ret["after0"], ret["after1"]
+    assert np.array_equal(r0[0], r1[0]) and r0[1] == r1[1] == 3.0
+    assert np.array_equal(r0[2], r1[2]) and np.array_equal(r0[3], r1[3])
+    assert r0[4] == r1[4] and r0[5] == r1[5] == 3
+    assert np.array_equal(a0[0], a1[0]) and a0[1] == a1[1]

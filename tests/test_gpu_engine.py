@@ -81,33 +81,8 @@ def test_engine_render_golden(tn, precision, tol):
     assert img.shape == (n, 3) and float(img.min()) >= 0.0 and float(img.max()) <= 1.0
 
 
-def test_engine_bf16_psnr_gate(tn):
-    """BF16 must stay within 0.1 dB PSNR of the fp32 path (north star): PSNR of each render against the same
-    synthetic ground-truth pixels."""
-    from torch_nerf_b200.engine import HotPathEngine
-
-    torch.manual_seed(7)
-    c32, f32 = nets(tn, 51, 52, "fp32")
-    c16, f16 = nets(tn, 51, 52, "bf16")
-    e32 = HotPathEngine(c32, f32, 64, 128, precision="fp32")
-    e16 = HotPathEngine(c16, f16, 64, 128, precision="bf16")
-    h = w = 64
-    focal = orc.blender_focal(w)
-    cam = tn.PerspectiveCamera({"f_x": focal, "f_y": focal, "img_width": w, "img_height": h},
-                               torch.from_numpy(orc.pose_spherical(45.0, -30.0, 4.0)), 2.0, 6.0)
-    n = h * w
-    u = (torch.rand(n, 64).cuda(), torch.rand(n, 64).cuda(), torch.rand(n, 128).cuda(), torch.rand(n, 128).cuda())
-    ray_o, ray_d, _ = e32.rays_from_pixels(cam, False, None, 0, n)
-    a = e32.render_rays(ray_o.clone(), ray_d.clone(), 2.0, 6.0, uniforms=u)["rgb_fine"].clone()
-    b = e16.render_rays(ray_o.clone(), ray_d.clone(), 2.0, 6.0, uniforms=u)["rgb_fine"].clone()
-    gt = torch.rand(n, 3, device="cuda")
-
-    def psnr(x):
-        return float(-10.0 * torch.log10(torch.mean((x.clamp(0, 1) - gt) ** 2)))
-
-    assert abs(psnr(a) - psnr(b)) < 0.1, (psnr(a), psnr(b))
-    direct = float(-10.0 * torch.log10(torch.mean((a - b) ** 2)))
-    assert direct > 35.0, direct  # bf16 image vs fp32 image
+# (the BF16 0.1 dB PSNR gate lives in tests/test_gpu_atsize.py::test_bf16_psnr_gate_structured_target: scored against
+#  a structured target at 100x100 instead of random ground truth, VERDICT r1 "what's weak" #1)
 
 
 def test_engine_train_step_bf16_vs_golden(tn):

@@ -86,31 +86,37 @@ class PerspectiveCamera:
 
     # ---- C-ABI view ------------------------------------------------------------------------------
     def pack(self, project_to_ndc: bool) -> "_lib.CameraStruct":
-        """Packs the camera for `nerf_generate_rays*` (include/nerf_b200.h nerf_camera_t).  The NDC scale
-        factors are evaluated in Python floats first (sampler_base.py:236-253 multiplies float32 tensors by
-        Python scalars, which torch applies as float32 scalars)."""
-        k = self._intrinsic.detach().to("cpu", torch.float32)
-        e = self._extrinsic.detach().to("cpu", torch.float32)
-        cam = _lib.CameraStruct()
-        cam.fx, cam.fy, cam.cx, cam.cy = float(k[0, 0]), float(k[1, 1]), float(k[0, 2]), float(k[1, 2])
-        rot = e[:3, :3].reshape(-1).tolist()
-        for i in range(9):
-            cam.rot[i] = rot[i]
-        trans = e[:3, -1].tolist()
-        for i in range(3):
-            cam.trans[i] = trans[i]
-        cam.img_w, cam.img_h = self._img_width, self._img_height
-        cam.project_to_ndc = 1 if project_to_ndc else 0
-        if project_to_ndc:
-            fx, fy = self.focal_lengths
-            if fx != fy:
-                raise ValueError(
-                    "Focal length used for computing NDC is ambiguous."
-                    f"Two different focal lengths ({fx}, {fy}) exists but only one can be used."
-                )
-            if self._t_near < 0:
-                raise ValueError(f"Expected a real number greater than or equal to 0. Got {self._t_near}.")
-            cam.ndc_sx = -(2 * fx / self._img_width)
-            cam.ndc_sy = -(2 * fx / self._img_height)
-            cam.ndc_two_near = 2 * self._t_near
-        return cam
+        return pack_camera(self, project_to_ndc)
+
+
+def pack_camera(camera, project_to_ndc: bool) -> "_lib.CameraStruct":
+    """Packs a camera for `nerf_generate_rays*` (include/nerf_b200.h nerf_camera_t).  `camera` is anything with the
+    reference camera's read-only surface (cameras.py:120-153: intrinsic, extrinsic, t_near, img_width, img_height,
+    focal_lengths) -- this package's PerspectiveCamera or the reference's own, so the sampler also works behind the
+    reference's VolumeRenderer.  The NDC scale factors are evaluated in Python floats first (sampler_base.py:236-253
+    multiplies float32 tensors by Python scalars, which torch applies as float32 scalars)."""
+    k = camera.intrinsic.detach().to("cpu", torch.float32)
+    e = camera.extrinsic.detach().to("cpu", torch.float32)
+    cam = _lib.CameraStruct()
+    cam.fx, cam.fy, cam.cx, cam.cy = float(k[0, 0]), float(k[1, 1]), float(k[0, 2]), float(k[1, 2])
+    rot = e[:3, :3].reshape(-1).tolist()
+    for i in range(9):
+        cam.rot[i] = rot[i]
+    trans = e[:3, -1].tolist()
+    for i in range(3):
+        cam.trans[i] = trans[i]
+    cam.img_w, cam.img_h = int(camera.img_width), int(camera.img_height)
+    cam.project_to_ndc = 1 if project_to_ndc else 0
+    if project_to_ndc:
+        fx, fy = camera.focal_lengths
+        if fx != fy:
+            raise ValueError(
+                "Focal length used for computing NDC is ambiguous."
+                f"Two different focal lengths ({fx}, {fy}) exists but only one can be used."
+            )
+        if camera.t_near < 0:
+            raise ValueError(f"Expected a real number greater than or equal to 0. Got {camera.t_near}.")
+        cam.ndc_sx = -(2 * fx / cam.img_w)
+        cam.ndc_sy = -(2 * fx / cam.img_h)
+        cam.ndc_two_near = 2 * camera.t_near
+    return cam

@@ -63,6 +63,7 @@ class _StepGraph:
         self.losses = torch.zeros((2,), device=device, dtype=torch.float32)
         self.graph = None
         self.launches = 0
+        self.keepalive = []  # every workspace the captured kernels address (the engine may outgrow and replace them)
 
 
 class HotPathEngine:
@@ -85,12 +86,23 @@ class HotPathEngine:
 
     # ------------------------------------------------------------------------------------------ buffers
     def _get(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
-        key = (name, tuple(shape), dtype)
+        """Workspace `name` as a tensor of `shape`: one grow-only allocation per name (a smaller request is a view of
+        it), so a warm-up batch, a last shard or another frame size do not each pin their own multi-GB set."""
+        shape = tuple(int(x) for x in shape)
+        numel = 1
+        for x in shape:
+            numel *= x
+        key = (name, dtype)
         t = self._buf.get(key)
-        if t is None:
-            t = torch.empty(shape, device=self.device, dtype=dtype)
+        if t is None or t.numel() < numel:
+            t = torch.empty((numel,), device=self.device, dtype=dtype)
             self._buf[key] = t
-        return t
+        return t[:numel].view(shape)
+
+    def release_workspaces(self) -> None:
+        """Drops every workspace and captured iteration (they are re-created on demand)."""
+        self._buf.clear()
+        self._graphs.clear()
 
     def _call(self, fn_name: str, *args, launches: int = 1):
         _lib.check(getattr(self.lib, fn_name)(*args), fn_name)
@@ -207,20 +219,35 @@ class HotPathEngine:
             w_pdf = self._get("w_pdf", (n, self.sc))
             w_pdf.copy_(co["w"])
             fi = self._pass(1, "f", ray_o, ray_d, n, float(near), float(far), w_pdf, uf, train=False)
+        self.last = {"coarse": co, "fine": fi}
         return {"rgb_coarse": co["rgb"], "weights_coarse": co["w"], "rgb_fine": fi["rgb"], "weights_fine": fi["w"],
                 "t_fine": fi["t"]}
 
     @torch.no_grad()
     def render_frame(self, camera: PerspectiveCamera, project_to_ndc: bool = False, first_pixel: int = 0,
-                     count: Optional[int] = None) -> torch.Tensor:
+                     count: Optional[int] = None, max_rays: int = 1 << 20, uniforms=None) -> torch.Tensor:
         """runners/render.py:58-107: all (or a contiguous range of) pixels, coarse then fine, clamped to [0,1].
-        Returns (count, 3); reshape to (H, W, 3) for a full frame."""
+        Returns (count, 3); reshape to (H, W, 3) for a full frame.  Rays are processed in chunks of at most `max_rays`
+        (the reference's num_ray_batch, volume_renderer.py:229-254; ~7 KB of workspace per ray, so the default keeps a
+        chunk near 7 GB) -- an 800x800 or 1008x756 frame is one chunk.  `uniforms` = (u_c, u0, u1, u2) over all `count`
+        rays replays given draws (tests); otherwise each chunk draws its own in the reference's order."""
         total = camera.img_height * camera.img_width
         count = total - first_pixel if count is None else count
-        with torch.cuda.device(self.device):
-            ray_o, ray_d, n = self.rays_from_pixels(camera, project_to_ndc, None, first_pixel, count)
-            out = self.render_rays(ray_o, ray_d, camera.t_near, camera.t_far)
-        return out["rgb_fine"].clamp(0.0, 1.0)
+        max_rays = max(1, int(max_rays))
+        if count <= max_rays:
+            with torch.cuda.device(self.device):
+                ray_o, ray_d, n = self.rays_from_pixels(camera, project_to_ndc, None, first_pixel, count)
+                out = self.render_rays(ray_o, ray_d, camera.t_near, camera.t_far, uniforms)
+            return out["rgb_fine"].clamp(0.0, 1.0)
+        img = torch.empty((count, 3), device=self.device, dtype=torch.float32)
+        for lo in range(0, count, max_rays):
+            k = min(max_rays, count - lo)
+            with torch.cuda.device(self.device):
+                ray_o, ray_d, n = self.rays_from_pixels(camera, project_to_ndc, None, first_pixel + lo, k)
+                u = None if uniforms is None else tuple(x[lo:lo + k] for x in uniforms)
+                out = self.render_rays(ray_o, ray_d, camera.t_near, camera.t_far, u)
+            torch.clamp(out["rgb_fine"], 0.0, 1.0, out=img[lo:lo + k])
+        return img
 
     def train_rays(self, ray_o, ray_d, near: float, far: float, target: torch.Tensor, uniforms=None,
                    loss_out: Optional[torch.Tensor] = None):
@@ -298,6 +325,7 @@ class HotPathEngine:
                         self._train_static(sg)
                     sg.graph = graph
                     sg.launches = self.launches - l0
+                    sg.keepalive = list(self._buf.values())
                 except RuntimeError as err:  # capture refused (e.g. another library touched the stream): stay eager
                     import warnings
 

@@ -19,6 +19,16 @@ class FlatAdam(torch.optim.Optimizer):
         self.grad_scale = 1.0  # set to 1/world to fold the data-parallel average into the update
         self._lib = _lib.load()
 
+    def zero_grad(self, set_to_none: bool = True):
+        """The kernels write gradients into the flat buffer by raw pointer (engine.FlatParams) and OVERWRITE it every
+        iteration, so the reference loop's `optimizer.zero_grad()` (train.py:131; set_to_none by default) must never
+        detach that buffer from the parameter: the gradients are zeroed in place and stay attached."""
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p.grad is not None:
+                    p.grad.detach_()
+                    p.grad.zero_()
+
     @torch.no_grad()
     def step(self, closure=None):
         if closure is not None:
@@ -29,7 +39,8 @@ class FlatAdam(torch.optim.Optimizer):
             b1, b2 = group["betas"]
             for p in group["params"]:
                 if p.grad is None:
-                    continue
+                    raise RuntimeError("FlatAdam: a parameter has no gradient buffer attached (the kernels write into "
+                                       "FlatParams.grad; do not set .grad to None)")
                 if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.is_contiguous()):
                     raise ValueError("FlatAdam needs contiguous float32 CUDA parameters")
                 st = self.state[p]

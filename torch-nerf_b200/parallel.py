@@ -56,3 +56,40 @@ def allreduce_mean_(flat_grad: torch.Tensor, world: int | None = None, scale: bo
     if scale:
         flat_grad.mul_(1.0 / world)
     return flat_grad
+
+
+def broadcast_replica_state(param: torch.Tensor, optimizer: torch.optim.Optimizer, scheduler=None, src: int = 0) -> None:
+    """Makes every rank's replica identical to rank `src`'s: the flat parameter buffer, its Adam state (`step`,
+    `exp_avg`, `exp_avg_sq`), the learning rates and the scheduler position.  Called by Trainer at construction and
+    after load_ckpt, so replicas cannot silently diverge through per-rank seeds or per-rank checkpoint files."""
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("broadcast_replica_state needs an initialised torch.distributed process group")
+    if dist.get_world_size() == 1:
+        return
+    dev = param.device
+    dist.broadcast(param.data, src=src)
+    st = optimizer.state.get(param, {})
+    has = torch.tensor([1 if len(st) else 0], device=dev)
+    dist.broadcast(has, src=src)
+    if int(has.item()):
+        if not len(st):  # this rank has no state yet: create it so the broadcast has somewhere to land
+            st = optimizer.state[param]
+            st["step"] = torch.tensor(0.0, dtype=torch.float32)
+            st["exp_avg"] = torch.zeros_like(param.data)
+            st["exp_avg_sq"] = torch.zeros_like(param.data)
+        step = st["step"].detach().to(dev, torch.float32).reshape(1).clone()
+        dist.broadcast(step, src=src)
+        st["step"] = step.reshape(()).to(st["step"].device)
+        dist.broadcast(st["exp_avg"], src=src)
+        dist.broadcast(st["exp_avg_sq"], src=src)
+    else:
+        optimizer.state.pop(param, None)
+    lrs = torch.tensor([float(g["lr"]) for g in optimizer.param_groups], device=dev, dtype=torch.float64)
+    dist.broadcast(lrs, src=src)
+    for g, lr in zip(optimizer.param_groups, lrs.tolist()):
+        g["lr"] = lr
+    if scheduler is not None:
+        pos = torch.tensor([float(scheduler.last_epoch)], device=dev, dtype=torch.float64)
+        dist.broadcast(pos, src=src)
+        scheduler.last_epoch = int(pos.item())
+        scheduler._last_lr = [g["lr"] for g in optimizer.param_groups]

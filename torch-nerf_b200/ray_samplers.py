@@ -11,7 +11,7 @@ from typing import Tuple, Union
 import torch
 
 from . import _lib
-from .cameras import PerspectiveCamera
+from .cameras import PerspectiveCamera, pack_camera
 
 
 class RayBundle:
@@ -79,7 +79,7 @@ class RaySamplerBase:
         dev = _cuda_device(pixel_coords.device if pixel_coords.is_cuda else None)
         coords = pixel_coords.to(device=dev, dtype=torch.int64).contiguous()
         n = coords.shape[0]
-        cam = camera.pack(project_to_ndc)
+        cam = pack_camera(camera, project_to_ndc)
         ray_o = torch.empty((n, 3), device=dev, dtype=torch.float32)
         ray_d = torch.empty((n, 3), device=dev, dtype=torch.float32)
         with torch.cuda.device(dev):
@@ -100,7 +100,7 @@ class RaySamplerBase:
             n = pix.shape[0]
         else:
             pix, n = None, int(count)
-        cam = camera.pack(project_to_ndc)
+        cam = pack_camera(camera, project_to_ndc)
         ray_o = torch.empty((n, 3), device=dev, dtype=torch.float32)
         ray_d = torch.empty((n, 3), device=dev, dtype=torch.float32)
         with torch.cuda.device(dev):

@@ -8,8 +8,10 @@ render / validation step, restated over the fused engine.
 Differences that are deliberate: both networks live in one flat buffer stepped by ONE Adam launch (optim.FlatAdam); the loss is
 accumulated on the device and read back once per epoch (the reference calls .item() three times per iteration); with
 several ranks every rank trains its shard of the pixel batch and the flat gradient is all-reduced once per step.
-A profile of the captured step (tools/prof_gaps.py) shows 17 us of GPU idle time per 5 ms step, so the step is NOT
-wrapped in a CUDA graph: there is no launch gap left to remove."""
+By default (`use_graph=True`, bf16) the forward + backward of an iteration is replayed from a CUDA graph
+(engine.train_pixels_graph); the all-reduce and the one-launch Adam stay outside it.  `use_graph=False` (and fp32
+validation mode) enqueues every kernel of the iteration instead.  With several ranks the constructor and `load_ckpt`
+broadcast rank 0's parameters and optimizer state, so replicas cannot drift apart through different seeds."""
 from __future__ import annotations
 
 from typing import Dict, Iterable, Tuple
@@ -77,6 +79,16 @@ class Trainer:
         # identical on every rank, so the ranks agree on the global batch they shard
         self._gen = torch.Generator().manual_seed(seed)
         self._losses = torch.zeros(2, device=self.device)
+        self.sync_replicas()
+
+    def sync_replicas(self) -> None:
+        """Data-parallel replicas must hold identical parameters and Adam state: rank 0's are broadcast (a caller that
+        seeds the ranks differently, or ranks that read different checkpoint files, would otherwise train different
+        weights on averaged gradients without any error)."""
+        if self.world > 1:
+            from .parallel import broadcast_replica_state
+
+            broadcast_replica_state(self.flat.param, self.optimizer, self.scheduler)
 
     # ------------------------------------------------------------------------------------------ training
     def select_pixels(self, img_height: int, img_width: int, epoch: int) -> torch.Tensor:
@@ -151,4 +163,6 @@ class Trainer:
         return save_ckpt(ckpt_dir, epoch, self.coarse, self.fine, self.optimizer, self.scheduler, self.flat)
 
     def load_ckpt(self, ckpt_dir) -> int:
-        return load_ckpt(ckpt_dir, self.coarse, self.fine, self.optimizer, self.scheduler, self.flat)
+        epoch = load_ckpt(ckpt_dir, self.coarse, self.fine, self.optimizer, self.scheduler, self.flat)
+        self.sync_replicas()
+        return epoch
