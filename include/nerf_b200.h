@@ -144,6 +144,20 @@ int nerf_adam_step(float* param_dev, const float* grad_dev, float* exp_avg_dev, 
 int nerf_mse_loss(const float* rgb_dev, const float* target_dev, int64_t n, float* g_rgb_dev,
                   float* loss_accum_dev, nerf_stream_t stream);
 
+/* Data-parallel step over NVLink peer memory: gradient exchange fused with the optimizer (csrc/dp_exchange.cu; SURVEY 8e --
+ * the reference is single-device, runner_utils.py:431-453).  ONE launch per rank and step does what "all-reduce the flat
+ * gradient buffer, then nerf_adam_step" does: entry barrier over peer-mapped flag words, rank k sums slice k of every rank's
+ * gradient buffer with P2P loads (fixed rank order: bit-identical sums on all replicas) and stores it into slice k of every
+ * buffer with P2P stores, barrier, then Adam over ALL parameters from the reduced local buffer (math of nerf_adam_step).
+ *   grad_ptrs[r] : rank r's flat gradient buffer as mapped into this process (symmetric / peer memory), n floats padded to
+ *                  a multiple of 4, 16-byte aligned;  flag_ptrs[r] : rank r's pad of 2*world 32-bit flag words, zeroed once
+ *   seq          : 1, 2, 3, ... identical on all ranks, incremented every call;  counter_dev : one zeroed local word
+ * Every rank of the group must make the call; a peer that never arrives traps the kernel after ~4 s instead of hanging. */
+int nerf_dp_exchange_adam(float* const* grad_ptrs, uint32_t* const* flag_ptrs, int rank, int world, float* param_dev,
+                          float* exp_avg_dev, float* exp_avg_sq_dev, int64_t n, double lr, double beta1, double beta2,
+                          double eps, int64_t step, double grad_scale, uint32_t seq, uint32_t* counter_dev,
+                          nerf_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K5 / K6 NeRF MLP
  *   replaces NeRF.forward (src/network/nerf.py:65-121) and its autograd backward.

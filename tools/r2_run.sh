@@ -6,7 +6,8 @@ run() { local name=$1; local to=$2; shift 2; timeout $to "$@" > gpurun_out/$name
 : > gpurun_out/summary.txt
 for step in "$@"; do
   case $step in
-    tests) TAILN=8 run tests 1500 python -m pytest tests -q -m gpu -p no:cacheprovider -x ;;
+    tests) TAILN=25 run tests 1500 python -m pytest tests -q -m gpu -p no:cacheprovider -rA --tb=short ;;
+    testsnew) TAILN=40 run testsnew 1500 python -m pytest tests/test_gpu_atsize.py tests/test_gpu_dropin_reference.py -q -m gpu -p no:cacheprovider -rA --tb=short -s ;;
     smoke) TAILN=2 run smoke 300 python __graft_entry__.py --smoke ;;
     overlap) TAILN=40 run overlap 600 python tools/prof_overlap.py ;;
     overlapc) TAILN=40 run overlapc 600 python tools/prof_overlap.py 4096 64 ;;

@@ -56,6 +56,8 @@ _PROTOTYPES = {
     "nerf_composite_bwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P]),
     "nerf_mse_loss": (c_int, [_P, _P, c_int64, _P, _P, _P]),
     "nerf_adam_step": (c_int, [_P, _P, _P, _P, c_int64, c_double, c_double, c_double, c_double, c_int64, c_double, _P]),
+    "nerf_dp_exchange_adam": (c_int, [POINTER(_P), POINTER(_P), c_int, c_int, _P, _P, _P, c_int64, c_double, c_double, c_double,
+                                      c_double, c_int64, c_double, ctypes.c_uint32, _P, _P]),
     "nerf_mlp_f32_cache_floats": (c_size_t, [POINTER(MlpDims), c_int64]),
     "nerf_mlp_f32_bwd_scratch_floats": (c_size_t, [POINTER(MlpDims), c_int64]),
     "nerf_mlp_f32_forward": (c_int, [POINTER(MlpDims), POINTER(_P), _P, _P, c_int64, _P, _P, _P, _P]),

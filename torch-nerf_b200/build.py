@@ -18,7 +18,7 @@ LIB_DIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIB_DIR, "libnerf_b200.so")
 LIB_SELFTEST = os.path.join(LIB_DIR, "libnerf_b200_selftest.so")
 SOURCES = ["api.cu", "rays.cu", "encode_composite.cu", "mlp_f32.cu", "mlp_tc_pack.cu", "mlp_tc_fwd.cu", "mlp_tc_bwd.cu",
-           "optim.cu"]
+           "optim.cu", "dp_exchange.cu"]
 SELFTEST_SOURCES = ["mlp_tc_selftest.cu"]  # links against libnerf_b200.so (error string, SM count)
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
