@@ -420,12 +420,21 @@ def run_b200(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    n_rays = args.rays
+    # weak scaling (default): args.rays per GPU; --global-rays G (config C4 as written): G / world rays per GPU
+    if args.global_rays:
+        assert args.global_rays % world == 0, "--global-rays must be divisible by the number of GPUs"
+        n_rays = args.global_rays // world
+    else:
+        n_rays = args.rays
     torch.manual_seed(0)  # identical replicas of both networks on every rank
     coarse = tn.NeRF(63, 27, precision=args.precision).to(dev)
     fine = tn.NeRF(63, 27, precision=args.precision).to(dev)
     eng = HotPathEngine(coarse, fine, SC, SF, precision=args.precision)
-    flat = eng.enable_flat_params()
+    # N > 1: gradient exchange fused with Adam over NVLink peer memory (parallel.PeerExchange); falls back to NCCL
+    from torch_nerf_b200.parallel import make_exchange
+
+    px = make_exchange(2 * 595844, dev, world)
+    flat = eng.enable_flat_params(px.grad if px is not None else None)
     eng_render = eng if args.precision == "bf16" else HotPathEngine(coarse, fine, SC, SF, precision="bf16")
     # runner_utils.py:690-711: Adam(lr 5e-4, eps 1e-8), ExponentialLR gamma = (5e-5/5e-4)^(1/300000); one Adam over both
     # networks' parameters -- here as ONE flat parameter that all 44 tensors alias (elementwise-identical update)
@@ -433,6 +442,7 @@ def run_b200(args):
 
     opt = FlatAdam([flat.param], lr=5e-4, eps=1e-8)  # torch.optim.Adam's state and math, one kernel launch (csrc/optim.cu)
     opt.grad_scale = 1.0 / world
+    opt.exchange = px
     sched = torch.optim.lr_scheduler.ExponentialLR(opt, (5e-5 / 5e-4) ** (1.0 / 300000))
     torch.manual_seed(1234 + rank)  # per-rank uniform stream / pixels
     focal = blender_focal(IMG)
@@ -465,8 +475,9 @@ def run_b200(args):
             else:
                 pix, tgt = dev_pix[i], dev_tgt[i]
             losses = eng.train_pixels(cam, pix, tgt, False, loss_out=losses_dev)
-        allreduce_mean_(flat.grad, world, scale=False)  # one NCCL all-reduce (sum) of the 4.77 MB flat gradient buffer
-        opt.step()
+        if px is None:
+            allreduce_mean_(flat.grad, world, scale=False)  # one NCCL all-reduce (sum) of the 4.77 MB flat gradient buffer
+        opt.step()  # with the peer exchange: sum over the ranks + Adam in ONE launch (csrc/dp_exchange.cu)
         sched.step()
         if e2e:
             losses_host[i].copy_(losses, non_blocking=True)
@@ -495,11 +506,80 @@ def run_b200(args):
             ms = float(t.item())
         return ms, eng.launches - l0 + (total_steps - args.warmup)  # + one Adam launch per step
 
+    # ---- N > 1: the sharded step must equal the 1-rank step on the concatenated batch: every
+    #      rank takes its slice of ONE global pixel batch and ONE global uniform stream, the gradient buffers are summed
+    #      by the exchange that the timed loop uses, and rank 0 recomputes the whole batch alone
+    parity = None
+    if world > 1 and args.precision == "bf16":
+        gcpu = torch.Generator().manual_seed(4242)
+        G = n_rays * world
+        gpix = torch.randperm(IMG * IMG, generator=gcpu)[:G].to(dev)
+        gtgt = torch.rand((G, 3), generator=gcpu).to(dev)
+        gdev = torch.Generator(device=dev).manual_seed(4242)
+        gu = [torch.rand((G, k), device=dev, generator=gdev) for k in (SC, SC, SF, SF)]
+        lo, hi = rank * n_rays, (rank + 1) * n_rays
+        eng.train_pixels(cams[0], gpix[lo:hi].contiguous(), gtgt[lo:hi].contiguous(), False, uniforms=[u[lo:hi] for u in gu])
+        if px is not None:
+            px.allreduce_sum_()
+        else:
+            allreduce_mean_(flat.grad, world, scale=False)
+        summed = flat.grad.clone() / world
+        torch.cuda.synchronize()
+        if rank == 0:
+            eng.train_pixels(cams[0], gpix, gtgt, False, uniforms=gu)
+            ref = flat.grad
+            scale = float(ref.abs().max())
+            parity = {"global_rays": G, "max_abs_diff_over_max": float((summed - ref).abs().max()) / scale,
+                      "cosine": float(torch.dot(summed, ref) / (summed.norm() * ref.norm())),
+                      "what": "all-reduced gradients of the N sharded steps / N vs rank 0 recomputing the concatenated "
+                              "batch (same pixels, targets, and rows of one global uniform stream)"}
+        del gu, gpix, gtgt, summed
+        eng.release_workspaces()
+        torch.cuda.empty_cache()
+        dist.barrier()
+
     with ClockSampler(local) as clk:
         ms_dev, launches = timed(False)
         time.sleep(2.0)  # let the board return to its idle power state so both loops start from the same condition
         ms_e2e, _ = timed(True)
     clocks = clk.summary()
+    # ---- config C4 as written: a 32768-ray GLOBAL batch split over the GPUs (strong scaling), 5 steps after 3 warm-ups
+    c4 = None
+    if args.precision == "bf16" and not args.no_c4 and not args.global_rays and 32768 % world == 0:
+        nr4 = 32768 // world
+        g4 = torch.Generator().manual_seed(77 + rank)
+        pix4 = [torch.randperm(IMG * IMG, generator=g4)[:nr4].to(dev) for _ in range(8)]
+        tgt4 = [torch.rand((nr4, 3), generator=g4).to(dev) for _ in range(8)]
+
+        def step4(i):
+            eng.train_pixels_graph(cams[i % len(cams)], pix4[i], tgt4[i], False) if use_graph else \
+                eng.train_pixels(cams[i % len(cams)], pix4[i], tgt4[i], False, loss_out=losses_dev)
+            if px is None:
+                allreduce_mean_(flat.grad, world, scale=False)
+            opt.step()
+            sched.step()
+
+        for i in range(3):
+            step4(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(3, 8):
+            step4(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms4 = e0.elapsed_time(e1) / 5
+        if world > 1:
+            t4 = torch.tensor([ms4], device=dev)
+            dist.all_reduce(t4, op=dist.ReduceOp.MAX)
+            ms4 = float(t4.item())
+        c4 = {"global_rays": 32768, "rays_per_gpu": nr4, "n_gpus": world, "ms_per_step": ms4, "rays_per_s": 32768 / (ms4 * 1e-3),
+              "scaling": "strong", "steps": 5}
+        del pix4, tgt4
+        eng.release_workspaces()
+        torch.cuda.empty_cache()
     rays_total = n_rays * world * args.steps
     value = rays_total / (ms_dev * 1e-3)
     e2e_value = rays_total / (ms_e2e * 1e-3)
@@ -703,18 +783,23 @@ def run_b200(args):
         step_flop = n_rays * (SC + SC + SF) * FLOP_TRAIN_PER_EVAL
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong" if args.global_rays else "weak",
+            "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": f"single training step (coarse 64 + fine 64+128, fwd+bwd, Adam), {n_rays}-ray batch per GPU, "
                                    "lego-shaped synthetic scene, 800x800 cameras, near/far 2/6",
                        "rays_per_gpu": n_rays, "global_rays": n_rays * world, "samples": [SC, SF],
                        "l2_policy": "per-step working set (activation cache + gradients, >1 GB) exceeds the 126 MB L2",
-                       "precision": args.precision, "cuda_graph": bool(use_graph)},
+                       "precision": args.precision, "cuda_graph": bool(use_graph),
+                       "exchange": "none (1 GPU)" if world == 1 else
+                                   ("peer-memory reduce + Adam in one kernel (csrc/dp_exchange.cu)" if px is not None
+                                    else "NCCL all-reduce + Adam")},
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n_rays * 8 + n_rays * 12,
                     "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks,
             "step_tensor_frac_sustained": step_flop / (ms_dev / args.steps * 1e-3) / 1e12 / pk["tf_sustained"],
-            "roofline": roof, "roofline_mlp": roof_mlp, "roofline_stages": stages, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "dropin": dropin,
+            "roofline": roof, "roofline_mlp": roof_mlp, "roofline_stages": stages, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "dropin": dropin, "dp_parity": parity,
+            "c4_global_32768": c4,
             "render": render,
             "loss_last": [float(x) for x in losses_host[total_steps - 1]],
         }
@@ -730,7 +815,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default=os.environ.get("NERF_B200_PRECISION", "bf16"), choices=["bf16", "fp32"])
-    ap.add_argument("--rays", type=int, default=4096)
+    ap.add_argument("--rays", type=int, default=4096, help="rays per GPU (weak scaling)")
+    ap.add_argument("--global-rays", type=int, default=0, help="global batch split over the GPUs (config C4: 32768); strong scaling")
+    ap.add_argument("--no-c4", action="store_true", help="skip the extra 32768-ray global-batch timing")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip the same-box torch-CUDA run of the unmodified reference")
     ap.add_argument("--no-dropin", action="store_true", help="skip timing the reference-facing plugin API (VolumeRenderer.render_scene)")

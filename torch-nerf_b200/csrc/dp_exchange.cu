@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(kDpThreads, 1) dp_exchange_adam_kernel(DpArgs 
   // ---- C: every rank's slice has landed in this rank's buffer
   if (threadIdx.x < W) wait_flag(a.flags[R] + W + threadIdx.x, a.seq);
   __syncthreads();
-  // ---- D: Adam over all parameters (same arithmetic as adam_kernel, csrc/optim.cu)
+  // ---- D: Adam over all parameters (same arithmetic as adam_kernel, csrc/optim.cu); param == null: exchange only
+  if (a.param == nullptr) return;
   for (int64_t q = (int64_t)blockIdx.x * kDpThreads + threadIdx.x; q < quads; q += (int64_t)gridDim.x * kDpThreads) {
     const int64_t i4 = 4 * q;
     const float4 gv = ld_cg4(a.grad[R] + i4);
@@ -151,8 +152,8 @@ extern "C" int nerf_dp_exchange_adam(float* const* grad_ptrs, uint32_t* const* f
   using namespace nerf;
   NERF_CHECK_ARG(world >= 1 && world <= kDpMaxWorld && rank >= 0 && rank < world, "nerf_dp_exchange_adam: bad rank / world");
   NERF_CHECK_ARG(n > 0 && step >= 1 && seq >= 1, "nerf_dp_exchange_adam: n, step and seq must be positive");
-  NERF_CHECK_ARG(grad_ptrs && flag_ptrs && param_dev && exp_avg_dev && exp_avg_sq_dev && counter_dev,
-                 "nerf_dp_exchange_adam: null pointer");
+  NERF_CHECK_ARG(grad_ptrs && flag_ptrs && counter_dev, "nerf_dp_exchange_adam: null pointer");
+  NERF_CHECK_ARG(param_dev == nullptr || (exp_avg_dev && exp_avg_sq_dev), "nerf_dp_exchange_adam: null optimizer state");
   DpArgs a;
   for (int r = 0; r < world; ++r) {
     NERF_CHECK_ARG(grad_ptrs[r] && flag_ptrs[r], "nerf_dp_exchange_adam: null peer pointer");

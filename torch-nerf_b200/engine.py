@@ -24,13 +24,19 @@ class FlatParams:
     buffer), so the data-parallel exchange is a single all-reduce over 2 x 595 844 floats and the kernels write
     gradients straight into it."""
 
-    def __init__(self, nets: Sequence[NeRF]):
+    def __init__(self, nets: Sequence[NeRF], grad_buffer: Optional[torch.Tensor] = None):
         self.nets = list(nets)
         params = [p for net in self.nets for p in net.ordered_parameters()]
         dev = params[0].device
         total = sum(p.numel() for p in params)
         self.flat = torch.empty(total, device=dev, dtype=torch.float32)
-        self.grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        if grad_buffer is None:
+            self.grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        else:  # e.g. parallel.PeerExchange.grad: symmetric memory the other ranks read over NVLink
+            if grad_buffer.shape != (total,) or grad_buffer.dtype != torch.float32 or grad_buffer.device != dev:
+                raise ValueError(f"grad_buffer must be a float32 tensor of {total} elements on {dev}")
+            self.grad = grad_buffer
+            self.grad.zero_()
         off = 0
         self.grad_views = []
         for p in params:
@@ -108,9 +114,11 @@ class HotPathEngine:
         _lib.check(getattr(self.lib, fn_name)(*args), fn_name)
         self.launches += launches
 
-    def enable_flat_params(self) -> FlatParams:
+    def enable_flat_params(self, grad_buffer: Optional[torch.Tensor] = None) -> FlatParams:
         if self.flat is None:
-            self.flat = FlatParams(self.nets)
+            self.flat = FlatParams(self.nets, grad_buffer)
+        elif grad_buffer is not None and grad_buffer.data_ptr() != self.flat.grad.data_ptr():
+            raise RuntimeError("flat parameters already exist with another gradient buffer")
         return self.flat
 
     # ------------------------------------------------------------------------------------------ pieces

@@ -17,6 +17,7 @@ class FlatAdam(torch.optim.Optimizer):
                         capturable=False, differentiable=False, fused=None, decoupled_weight_decay=False)
         super().__init__(params, defaults)
         self.grad_scale = 1.0  # set to 1/world to fold the data-parallel average into the update
+        self.exchange = None   # parallel.PeerExchange: step() then sums the ranks' gradients AND updates in one launch
         self._lib = _lib.load()
 
     def zero_grad(self, set_to_none: bool = True):
@@ -49,6 +50,10 @@ class FlatAdam(torch.optim.Optimizer):
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 st["step"] += 1
+                if self.exchange is not None:
+                    self.exchange.step(p, st["exp_avg"], st["exp_avg_sq"], float(group["lr"]), b1, b2, group["eps"],
+                                       int(st["step"]), float(self.grad_scale))
+                    continue
                 with torch.cuda.device(p.device):
                     _lib.check(self._lib.nerf_adam_step(_lib.ptr(p), _lib.ptr(p.grad), _lib.ptr(st["exp_avg"]),
                                                         _lib.ptr(st["exp_avg_sq"]), p.numel(), float(group["lr"]), b1, b2,

@@ -93,3 +93,99 @@ def broadcast_replica_state(param: torch.Tensor, optimizer: torch.optim.Optimize
         dist.broadcast(pos, src=src)
         scheduler.last_epoch = int(pos.item())
         scheduler._last_lr = [g["lr"] for g in optimizer.param_groups]
+
+
+class PeerExchange:
+    """The data-parallel step as ONE kernel over NVLink peer memory (csrc/dp_exchange.cu, nerf_dp_exchange_adam): the flat
+    gradient buffer lives in symmetric memory every rank maps, each rank reduces its slice of all buffers with P2P loads,
+    stores the sum back into all of them with P2P stores, and runs Adam -- instead of an NCCL all-reduce followed by an
+    optimizer launch.  Construction is collective (every rank of `group`); it raises when symmetric memory is not
+    available on the box, and callers then stay on `allreduce_mean_` + FlatAdam.
+
+        px = PeerExchange(numel, device)          # px.grad: the flat gradient buffer the kernels must write into
+        flat = engine.enable_flat_params(grad_buffer=px.grad)
+        opt = FlatAdam([flat.param], ...); opt.exchange = px     # opt.step() now makes the fused call
+    """
+
+    def __init__(self, numel: int, device: torch.device, group=None):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm
+
+        from . import _lib
+
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerExchange needs an initialised torch.distributed process group")
+        group = dist.group.WORLD if group is None else group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 16:
+            raise RuntimeError("PeerExchange supports up to 16 ranks of one NVLink domain")
+        self.numel = int(numel)
+        padded = (self.numel + 3) // 4 * 4
+        try:  # older torch releases want the group registered first; newer ones deprecate the call
+            symm.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass
+        with torch.cuda.device(device):
+            self._grad_full = symm.empty(padded, dtype=torch.float32, device=device)
+            self._flags = symm.empty(64, dtype=torch.int32, device=device)
+            self._grad_full.zero_()
+            self._flags.zero_()
+            self._h_grad = symm.rendezvous(self._grad_full, group.group_name)
+            self._h_flags = symm.rendezvous(self._flags, group.group_name)
+            self.counter = torch.zeros(1, device=device, dtype=torch.int32)
+            torch.cuda.synchronize(device)
+        dist.barrier(group)  # every pad is zero before anybody's first kernel writes a flag
+        self.grad = self._grad_full[: self.numel]
+        self._grad_ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in self._h_grad.buffer_ptrs])
+        self._flag_ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in self._h_flags.buffer_ptrs])
+        self.seq = 0
+        self._lib = _lib.load()
+        self.device = device
+
+    def step(self, param: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, lr: float, beta1: float, beta2: float,
+             eps: float, step: int, grad_scale: float) -> None:
+        """Collective: sums the gradient buffers of all ranks and applies Adam update number `step` (1-based)."""
+        from . import _lib
+
+        if param.grad is None or param.grad.data_ptr() != self.grad.data_ptr():
+            raise RuntimeError("PeerExchange: the parameter's gradient is not the symmetric buffer (use "
+                               "engine.enable_flat_params(grad_buffer=px.grad))")
+        self.seq += 1
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.nerf_dp_exchange_adam(self._grad_ptrs, self._flag_ptrs, self.rank, self.world, _lib.ptr(param),
+                                                       _lib.ptr(exp_avg), _lib.ptr(exp_avg_sq), self.numel, float(lr), float(beta1),
+                                                       float(beta2), float(eps), int(step), float(grad_scale), self.seq,
+                                                       _lib.ptr(self.counter, torch.int32), _lib.stream()),
+                       "nerf_dp_exchange_adam")
+
+
+    def allreduce_sum_(self) -> torch.Tensor:
+        """Collective: the exchange alone -- every rank's `grad` ends up holding the sum over the ranks (no update)."""
+        from . import _lib
+
+        self.seq += 1
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.nerf_dp_exchange_adam(self._grad_ptrs, self._flag_ptrs, self.rank, self.world, None, None, None,
+                                                       self.numel, 0.0, 0.9, 0.999, 1e-8, 1, 1.0, self.seq,
+                                                       _lib.ptr(self.counter, torch.int32), _lib.stream()),
+                       "nerf_dp_exchange_adam")
+        return self.grad
+
+
+def make_exchange(numel: int, device: torch.device, world: int):
+    """PeerExchange when the box supports it (world > 1, symmetric memory), else None -> NCCL all-reduce + FlatAdam."""
+    if world <= 1 or os.environ.get("NERF_B200_EXCHANGE", "peer") == "nccl":
+        return None
+    ok = 1
+    px = None
+    try:
+        px = PeerExchange(numel, device)
+    except Exception as err:  # noqa: BLE001 -- any failure (no symmetric memory, no P2P) selects the NCCL path
+        import warnings
+
+        warnings.warn(f"PeerExchange unavailable, using NCCL all-reduce + Adam: {type(err).__name__}: {err}")
+        ok = 0
+    flag = torch.tensor([ok], device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # all ranks or none
+    return px if int(flag.item()) == 1 else None

@@ -65,7 +65,13 @@ class Trainer:
 
         self.coarse, self.fine = coarse, fine
         self.engine = HotPathEngine(coarse, fine, num_samples_coarse, num_samples_fine, precision)
-        self.flat = self.engine.enable_flat_params()
+        # several ranks: the flat gradient buffer lives in symmetric memory and the exchange is fused with Adam
+        # (parallel.PeerExchange); None (single rank, or no symmetric memory) -> NCCL all-reduce + one Adam launch
+        from .parallel import make_exchange
+
+        numel = sum(p.numel() for net in (coarse, fine) for p in net.parameters())
+        self.exchange = make_exchange(numel, self.engine.device, int(world))
+        self.flat = self.engine.enable_flat_params(self.exchange.grad if self.exchange is not None else None)
         self.num_pixels = int(num_pixels)
         self.t_near, self.t_far, self.project_to_ndc = float(t_near), float(t_far), bool(project_to_ndc)
         self.rank, self.world = int(rank), int(world)
@@ -73,6 +79,7 @@ class Trainer:
 
         self.optimizer = FlatAdam([self.flat.param], lr=init_lr, eps=eps)  # torch.optim.Adam's state layout, one launch
         self.optimizer.grad_scale = 1.0 / self.world
+        self.optimizer.exchange = self.exchange
         self.scheduler = torch.optim.lr_scheduler.ExponentialLR(self.optimizer, exp_lr_gamma(init_lr, end_lr, num_iter))
         self.device = self.engine.device
         # pixel selection is host-side in the reference (np.random.choice / torch.randperm on CPU): one generator,
@@ -115,8 +122,9 @@ class Trainer:
             losses = self.engine.train_pixels(camera, pix.to(self.device, non_blocking=True),
                                               tgt.to(self.device, non_blocking=True), self.project_to_ndc,
                                               loss_out=self._losses)
-        allreduce_mean_(self.flat.grad, self.world, scale=False)  # the 1/world rides on the Adam kernel
-        self.optimizer.step()
+        if self.exchange is None:
+            allreduce_mean_(self.flat.grad, self.world, scale=False)  # the 1/world rides on the Adam kernel
+        self.optimizer.step()  # with a PeerExchange: gradient sum over the ranks + Adam in one launch
         self.scheduler.step()
         return losses
 
