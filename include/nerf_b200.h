@@ -131,6 +131,13 @@ int nerf_composite_bwd(const float* sigma_dev, const float* radiance_dev, const 
                        const float* g_rgb_dev, const float* g_w_dev, int64_t n, int s, float* g_sigma_dev,
                        float* g_radiance_dev, nerf_stream_t stream);
 
+/* Training-step form of the above (train.py:180/202 + runner_utils.py:731): rgb_dev (N,3) is the rendered colour and
+ * target_dev (N,3) the ground truth; the MSE head is folded in -- g_rgb = 2/(3N)(rgb - target) never goes to memory and
+ * *loss_accum_dev += mean((rgb - target)^2).  s <= 256. */
+int nerf_composite_bwd_mse(const float* sigma_dev, const float* radiance_dev, const float* delta_dev, const float* rgb_dev,
+                           const float* target_dev, int64_t n, int s, float* g_sigma_dev, float* g_radiance_dev,
+                           float* loss_accum_dev, nerf_stream_t stream);
+
 /* Adam update of a flat fp32 parameter buffer (torch.optim.Adam as set up at runners/runner_utils.py:691-695: lr, eps
  * given; betas, weight_decay = 0, amsgrad = False defaults), update number `step` (1-based):
  *   g = grad * grad_scale;  m += (1 - beta1)(g - m);  v = beta2 v + (1 - beta2) g^2;
@@ -193,6 +200,11 @@ int nerf_mlp_f32_backward(const nerf_mlp_dims_t* dims, const float* const* param
 size_t nerf_mlp_bf16_packed_bytes(void);
 /* re-pack after every optimizer step */
 int nerf_mlp_bf16_pack(const float* const* params, void* packed_dev, nerf_stream_t stream);
+/* Prologue of a training iteration in ONE launch: nerf_mlp_bf16_pack of TWO networks (the coarse and the fine one,
+ * runner_utils.py:569-660) plus the zero fill of two float buffers (the flat gradient buffer the weight-gradient kernels
+ * accumulate into, the loss accumulators); either zero region may be empty. */
+int nerf_train_prologue(const float* const* params_a, void* packed_a_dev, const float* const* params_b, void* packed_b_dev,
+                        float* zero0_dev, int64_t zero0_count, float* zero1_dev, int64_t zero1_count, nerf_stream_t stream);
 /* bytes of per-call training cache for m rows (saved activations in tile-image form + relu masks) */
 size_t nerf_mlp_bf16_cache_bytes(int64_t m);
 /* Fused query: positional encoding of pts/dirs (K4) is computed inside the kernel as the first layer's

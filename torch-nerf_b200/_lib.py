@@ -54,6 +54,8 @@ _PROTOTYPES = {
     "nerf_posenc": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, c_int64, _P]),
     "nerf_composite_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P]),
     "nerf_composite_bwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P]),
+    "nerf_composite_bwd_mse": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P, _P]),
+    "nerf_train_prologue": (c_int, [POINTER(_P), _P, POINTER(_P), _P, _P, c_int64, _P, c_int64, _P]),
     "nerf_mse_loss": (c_int, [_P, _P, c_int64, _P, _P, _P]),
     "nerf_adam_step": (c_int, [_P, _P, _P, _P, c_int64, c_double, c_double, c_double, c_double, c_int64, c_double, _P]),
     "nerf_dp_exchange_adam": (c_int, [POINTER(_P), POINTER(_P), c_int, c_int, _P, _P, _P, c_int64, c_double, c_double, c_double,

@@ -375,7 +375,8 @@ __global__ void __launch_bounds__(kCompWarps * 32, MB)
     composite_bwd_blk_kernel(const float* __restrict__ sigma, const float* __restrict__ radiance,
                              const float* __restrict__ delta, const float* __restrict__ g_rgb,
                              const float* __restrict__ g_w_ext, int64_t n, int s, float* __restrict__ g_sigma,
-                             float* __restrict__ g_radiance) {
+                             float* __restrict__ g_radiance, const float* __restrict__ mse_target, float inv_cnt,
+                             float* __restrict__ loss_accum) {
   using L = BlkLayout<G>;
   __shared__ float stage_all[kCompWarps][L::kWarpFloats];
   const int warp = threadIdx.x >> 5, lane = lane_id();
@@ -414,7 +415,15 @@ __global__ void __launch_bounds__(kCompWarps * 32, MB)
     __syncwarp();
     // blocked reads
     float x[G], dlb[G], gw[G];
-    const float gr = __ldg(g_rgb + 3 * ray), gg = __ldg(g_rgb + 3 * ray + 1), gb = __ldg(g_rgb + 3 * ray + 2);
+    // g_rgb is either given, or (training step) `g_rgb` holds the rendered colour and the MSE head is folded in here:
+    // g = 2/(3N) (rgb - target), loss += mean((rgb - target)^2)   (runner_utils.py:731, train.py:180/202)
+    float gr = __ldg(g_rgb + 3 * ray), gg = __ldg(g_rgb + 3 * ray + 1), gb = __ldg(g_rgb + 3 * ray + 2);
+    if (mse_target != nullptr) {
+      const float dr = gr - __ldg(mse_target + 3 * ray), dg = gg - __ldg(mse_target + 3 * ray + 1),
+                  db = gb - __ldg(mse_target + 3 * ray + 2);
+      gr = 2.0f * inv_cnt * dr, gg = 2.0f * inv_cnt * dg, gb = 2.0f * inv_cnt * db;
+      if (lane == 0) atomicAdd(loss_accum, (dr * dr + dg * dg + db * db) * inv_cnt);
+    }
 #pragma unroll
     for (int k = 0; k < G; ++k) {
       x[k] = s_sg[lane * L::kS1 + k];
@@ -509,13 +518,14 @@ static void launch_composite_fwd_reg(const float* sigma, const float* radiance, 
 template <int G>
 static void launch_composite_bwd_blk(const float* sigma, const float* radiance, const float* delta, const float* g_rgb,
                                      const float* g_w, int64_t n, int s, float* g_sigma, float* g_radiance,
-                                     cudaStream_t stream) {
+                                     cudaStream_t stream, const float* mse_target = nullptr, float inv_cnt = 0.f,
+                                     float* loss_accum = nullptr) {
   // 6 CTAs per SM (80 registers per thread) measured best for 192 samples: 945 us at the unconstrained 95 registers,
   // 866 us at 80, 875 us at 64 (640 000 rays)
   // CTAs per SM measured on 192 samples (640 000 rays): 5 -> 778 us, 6 -> 768 us, 7 (72 registers) -> 704 us, 8 -> 797 us
   constexpr int kMinBlocks = G <= 6 ? 7 : 4;
   composite_bwd_blk_kernel<G, kMinBlocks><<<(unsigned)ceil_div64(n, kCompWarps), kCompWarps * 32, 0, stream>>>(
-      sigma, radiance, delta, g_rgb, g_w, n, s, g_sigma, g_radiance);
+      sigma, radiance, delta, g_rgb, g_w, n, s, g_sigma, g_radiance, mse_target, inv_cnt, loss_accum);
 }
 
 }  // namespace nerf
@@ -578,6 +588,25 @@ int nerf_composite_bwd(const float* sigma_dev, const float* radiance_dev, const 
   else
     composite_bwd_kernel<<<(unsigned)ceil_div64(n, kCompWarps), kCompWarps * 32, 0, cs>>>(
         sigma_dev, radiance_dev, delta_dev, g_rgb_dev, g_w_dev, n, s, g_sigma_dev, g_radiance_dev);
+  NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
+
+// The training step's loss head folded into the compositing backward: rgb_dev (N,3) is the rendered colour, target_dev
+// (N,3) the ground truth; g_rgb = 2/(3N) (rgb - target) never goes to memory, *loss_accum_dev += mean((rgb - target)^2).
+int nerf_composite_bwd_mse(const float* sigma_dev, const float* radiance_dev, const float* delta_dev, const float* rgb_dev,
+                           const float* target_dev, int64_t n, int s, float* g_sigma_dev, float* g_radiance_dev,
+                           float* loss_accum_dev, nerf_stream_t stream) {
+  NERF_CHECK_ARG(n >= 0 && s > 0 && s <= 256, "nerf_composite_bwd_mse: samples per ray must be in [1,256]");
+  if (n == 0) return NERF_OK;
+  NERF_CHECK_ARG(sigma_dev && radiance_dev && delta_dev && rgb_dev && target_dev && g_sigma_dev && g_radiance_dev && loss_accum_dev,
+                 "nerf_composite_bwd_mse: null pointer");
+  cudaStream_t cs = as_stream(stream);
+  const float inv_cnt = 1.0f / (float)(3 * n);
+  if (s <= 64) launch_composite_bwd_blk<2>(sigma_dev, radiance_dev, delta_dev, rgb_dev, nullptr, n, s, g_sigma_dev, g_radiance_dev, cs, target_dev, inv_cnt, loss_accum_dev);
+  else if (s <= 128) launch_composite_bwd_blk<4>(sigma_dev, radiance_dev, delta_dev, rgb_dev, nullptr, n, s, g_sigma_dev, g_radiance_dev, cs, target_dev, inv_cnt, loss_accum_dev);
+  else if (s <= 192) launch_composite_bwd_blk<6>(sigma_dev, radiance_dev, delta_dev, rgb_dev, nullptr, n, s, g_sigma_dev, g_radiance_dev, cs, target_dev, inv_cnt, loss_accum_dev);
+  else launch_composite_bwd_blk<8>(sigma_dev, radiance_dev, delta_dev, rgb_dev, nullptr, n, s, g_sigma_dev, g_radiance_dev, cs, target_dev, inv_cnt, loss_accum_dev);
   NERF_LAUNCH_CHECK();
   return NERF_OK;
 }

@@ -23,10 +23,8 @@ struct PackChunk {
 constexpr int kMaxPackChunks = 160;
 __constant__ PackChunk c_pack[kMaxPackChunks];
 
-__global__ void __launch_bounds__(256) pack_weights_kernel(ParamPtrs params, uint8_t* __restrict__ packed) {
-  const PackChunk pc = c_pack[blockIdx.y];
-  int u = blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte unit (8 bf16) per thread
-  if (u >= pc.nrows * 8) return;
+__device__ __forceinline__ void pack_unit(const ParamPtrs& params, uint8_t* __restrict__ packed, const PackChunk& pc, int u) {
+  if (u >= pc.nrows * 8) return;  // one 16-byte unit (8 bf16) per thread
   int n = u >> 3, j = u & 7;
   const float* w = params.p[pc.param];
   uint32_t out[4];
@@ -48,8 +46,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(ParamPtrs params, uin
   *dst = make_uint4(out[0], out[1], out[2], out[3]);
 }
 
-__global__ void pack_consts_kernel(ParamPtrs params, float* __restrict__ c) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void pack_const(const ParamPtrs& params, float* __restrict__ c, int i) {
   if (i >= kCFloats) return;
   float v = 0.f;
   if (i < kCBias8) v = params.p[2 * (i >> 8) + 1][i & 255];   // biases of fc_in, fc_1..fc_7
@@ -60,6 +57,40 @@ __global__ void pack_consts_kernel(ParamPtrs params, float* __restrict__ c) {
   else if (i == kCB8_0) v = params.p[B_8][0];
   else if (i < kCBout + 3) v = params.p[B_OUT][i - kCBout];
   c[i] = v;
+}
+
+__global__ void __launch_bounds__(256) pack_weights_kernel(ParamPtrs params, uint8_t* __restrict__ packed) {
+  pack_unit(params, packed, c_pack[blockIdx.y], blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__global__ void pack_consts_kernel(ParamPtrs params, float* __restrict__ c) {
+  pack_const(params, c, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// Prologue of a training iteration in ONE launch: the bf16 images of BOTH networks (weights + constants) and the zero
+// fill of two buffers (the flat gradient buffer, the loss accumulators).  grid = (4, chunks + 4 + kZeroRows, 2):
+// blockIdx.z = network; blockIdx.y selects the role.
+constexpr int kZeroRows = 32;
+struct PrologueArgs {
+  ParamPtrs params[2];
+  uint8_t* packed[2];
+  float* zero_ptr[2];
+  int64_t zero_count[2];
+  int n_chunks;
+};
+__global__ void __launch_bounds__(256) train_prologue_kernel(PrologueArgs a) {
+  const int net = blockIdx.z, y = blockIdx.y;
+  if (y < a.n_chunks) {
+    pack_unit(a.params[net], a.packed[net], c_pack[y], blockIdx.x * blockDim.x + threadIdx.x);
+  } else if (y < a.n_chunks + 4) {
+    pack_const(a.params[net], reinterpret_cast<float*>(a.packed[net] + kPackedConstOff),
+               ((y - a.n_chunks) * 4 + blockIdx.x) * 256 + threadIdx.x);
+  } else {
+    float* z = a.zero_ptr[net];
+    const int64_t cnt = a.zero_count[net];
+    const int64_t stride = (int64_t)kZeroRows * 4 * 256;
+    for (int64_t i = ((int64_t)(y - a.n_chunks - 4) * 4 + blockIdx.x) * 256 + threadIdx.x; i < cnt; i += stride) z[i] = 0.f;
+  }
 }
 
 static int build_pack_table(PackChunk* t) {
@@ -134,6 +165,34 @@ int nerf_mlp_bf16_pack(const float* const* params, void* packed_dev, nerf_stream
   NERF_LAUNCH_CHECK();
   pack_consts_kernel<<<(kCFloats + 255) / 256, 256, 0, st>>>(
       pp, reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(packed_dev) + kPackedConstOff));
+  NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
+
+int nerf_train_prologue(const float* const* params_a, void* packed_a_dev, const float* const* params_b, void* packed_b_dev,
+                        float* zero0_dev, int64_t zero0_count, float* zero1_dev, int64_t zero1_count, nerf_stream_t stream) {
+  NERF_CHECK_ARG(params_a && packed_a_dev && params_b && packed_b_dev, "nerf_train_prologue: null pointer");
+  NERF_CHECK_ARG(zero0_count >= 0 && zero1_count >= 0 && (zero0_dev || zero0_count == 0) && (zero1_dev || zero1_count == 0),
+                 "nerf_train_prologue: bad zero-fill arguments");
+  int dev = 0;
+  NERF_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices || !g_pack_table_ready[dev]) {
+    PackChunk table[kMaxPackChunks];
+    g_pack_chunks = build_pack_table(table);
+    NERF_CUDA(cudaMemcpyToSymbol(c_pack, table, sizeof(PackChunk) * g_pack_chunks));
+    if (dev >= 0 && dev < kMaxDevices) g_pack_table_ready[dev] = true;
+  }
+  PrologueArgs a;
+  for (int i = 0; i < NERF_NUM_PARAM_TENSORS; ++i) {
+    NERF_CHECK_ARG(params_a[i] != nullptr && params_b[i] != nullptr, "nerf_train_prologue: null parameter pointer");
+    a.params[0].p[i] = const_cast<float*>(params_a[i]);
+    a.params[1].p[i] = const_cast<float*>(params_b[i]);
+  }
+  a.packed[0] = reinterpret_cast<uint8_t*>(packed_a_dev), a.packed[1] = reinterpret_cast<uint8_t*>(packed_b_dev);
+  a.zero_ptr[0] = zero0_dev, a.zero_ptr[1] = zero1_dev;
+  a.zero_count[0] = zero0_count, a.zero_count[1] = zero1_count;
+  a.n_chunks = g_pack_chunks;
+  train_prologue_kernel<<<dim3(4, g_pack_chunks + 4 + kZeroRows, 2), 256, 0, as_stream(stream)>>>(a);
   NERF_LAUNCH_CHECK();
   return NERF_OK;
 }

@@ -89,6 +89,7 @@ class HotPathEngine:
         self._buf: Dict[Tuple, torch.Tensor] = {}
         self._graphs: Dict[Tuple, _StepGraph] = {}
         self.launches = 0  # kernels of this library enqueued so far (host-side count)
+        self._prologue_done = False  # inside train_rays: both bf16 weight images are fresh, gradients and losses zeroed
 
     # ------------------------------------------------------------------------------------------ buffers
     def _get(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
@@ -169,7 +170,8 @@ class HotPathEngine:
         else:
             # with flat parameters an optimizer may have stepped the shared buffer without touching the per-tensor
             # version counters, so the bf16 image is rebuilt on every pass (2.3 MB, ~10 us)
-            packed = net.packed_weights(force=train or self.flat is not None)
+            # (a training iteration packs both networks in its one-launch prologue: nothing to do here then)
+            packed = net._packed if self._prologue_done else net.packed_weights(force=train or self.flat is not None)
             cache = None
             if train:
                 cache = self._get(tag + "cache16", (self.lib.nerf_mlp_bf16_cache_bytes(m),), torch.uint8)
@@ -182,15 +184,24 @@ class HotPathEngine:
         ctx["rgb"], ctx["w"] = rgb, w
         return ctx
 
-    def _backward(self, which: int, ctx, n: int, g_rgb, grads):
+    def _backward(self, which: int, ctx, n: int, g_rgb, grads, target=None, loss=None):
+        """Backward of one pass.  With `target` the MSE head is folded into the compositing backward (g_rgb is never
+        materialised, `loss` += the pass's MSE); otherwise `g_rgb` is the upstream gradient."""
         P, st = _lib.ptr, _lib.stream()
         net = self.nets[which]
         s, m = ctx["s"], ctx["m"]
         tag = "bc" if which == 0 else "bf"
         g_sigma = self._get(tag + "gs", (n, s))
         g_rad = self._get(tag + "gr", (n, s, 3))
-        self._call("nerf_composite_bwd", P(ctx["sigma"]), P(ctx["rad"]), P(ctx["delta"]), P(g_rgb), None, n, s, P(g_sigma),
-                   P(g_rad), st)
+        if target is not None and s <= 256:
+            self._call("nerf_composite_bwd_mse", P(ctx["sigma"]), P(ctx["rad"]), P(ctx["delta"]), P(ctx["rgb"]), P(target), n, s,
+                       P(g_sigma), P(g_rad), P(loss), st)
+        else:
+            if target is not None:
+                g_rgb = self._get(tag + "g_rgb", (n, 3))
+                self._call("nerf_mse_loss", P(ctx["rgb"]), P(target), n, P(g_rgb), P(loss), st)
+            self._call("nerf_composite_bwd", P(ctx["sigma"]), P(ctx["rad"]), P(ctx["delta"]), P(g_rgb), None, n, s, P(g_sigma),
+                       P(g_rad), st)
         garr = _lib.pointer_array(grads)
         if self.precision == "fp32":
             scratch = self._get("scratch32", (self.lib.nerf_mlp_f32_bwd_scratch_floats(net._dims, n * (self.sc + self.sf)),))
@@ -199,8 +210,12 @@ class HotPathEngine:
                        garr, P(scratch), st, launches=60)
         else:
             scratch = self._get("scratch16", (self.lib.nerf_mlp_bf16_bwd_scratch_bytes(n * (self.sc + self.sf)),), torch.uint8)
-            self._call("nerf_mlp_bf16_backward", P(net.packed_weights(), torch.uint8), P(ctx["cache"], torch.uint8),
-                       P(ctx["rad"]), m, P(g_sigma), P(g_rad), garr, P(scratch, torch.uint8), st, launches=4)
+            if self._prologue_done:  # gradients were zeroed by the prologue: chain + weight gradients only
+                self._call("nerf_mlp_bf16_backward_part", P(net._packed, torch.uint8), P(ctx["cache"], torch.uint8), P(ctx["rad"]),
+                           m, P(g_sigma), P(g_rad), garr, P(scratch, torch.uint8), 6, 0, (m + 127) // 128, 0, st, launches=2)
+            else:
+                self._call("nerf_mlp_bf16_backward", P(net.packed_weights(), torch.uint8), P(ctx["cache"], torch.uint8),
+                           P(ctx["rad"]), m, P(g_sigma), P(g_rad), garr, P(scratch, torch.uint8), st, launches=3)
 
     # ------------------------------------------------------------------------------------------ public
     def rays_from_pixels(self, camera: PerspectiveCamera, project_to_ndc: bool, pixel_indices: Optional[torch.Tensor],
@@ -260,28 +275,51 @@ class HotPathEngine:
     def train_rays(self, ray_o, ray_d, near: float, far: float, target: torch.Tensor, uniforms=None,
                    loss_out: Optional[torch.Tensor] = None):
         """Forward + backward of one training iteration (train.py:172-215) on given rays.  Gradients of both
-        networks are OVERWRITTEN in the flat gradient buffer; returns the device tensor [coarse_loss, fine_loss]."""
+        networks are OVERWRITTEN in the flat gradient buffer; returns the device tensor [coarse_loss, fine_loss].
+
+        bf16 mode keeps the launch count down (the iteration is ~1 % small kernels): ONE prologue launch packs both
+        networks' bf16 images and zeroes the gradients and the loss accumulators, the four uniform tensors come from one
+        draw, and the MSE head rides on the compositing backward."""
         P, st = _lib.ptr, _lib.stream()
         flat = self.enable_flat_params()
         n = ray_o.shape[0]
         near, far = float(near), float(far)
+        bf16 = self.precision == "bf16"
         with torch.cuda.device(self.device), torch.no_grad():
             losses = loss_out if loss_out is not None else self._get("losses", (2,))
-            losses.zero_()
-            uc = self._uniforms(n, None if uniforms is None else uniforms[:1], fine=False)
-            co = self._pass(0, "c", ray_o, ray_d, n, near, far, None, uc, train=True)
-            g_c = self._get("g_rgb_c", (n, 3))
-            self._call("nerf_mse_loss", P(co["rgb"]), P(target), n, P(g_c), P(losses[0:1]), st)
-            # the fine pass perturbs its copy of the coarse weights in place (utils.py:31)
-            w_pdf = self._get("w_pdf", (n, self.sc))
-            w_pdf.copy_(co["w"])
-            uf = self._uniforms(n, None if uniforms is None else uniforms[1:], fine=True)
-            fi = self._pass(1, "f", ray_o, ray_d, n, near, far, w_pdf, uf, train=True)
-            g_f = self._get("g_rgb_f", (n, 3))
-            self._call("nerf_mse_loss", P(fi["rgb"]), P(target), n, P(g_f), P(losses[1:2]), st)
-            # autograd order: the fine pass is differentiated first (train.py:190-215)
-            self._backward(1, fi, n, g_f, flat.grads_of(1))
-            self._backward(0, co, n, g_c, flat.grads_of(0))
+            if bf16:
+                c, f = self.nets
+                for net in self.nets:
+                    if net._packed is None or net._packed.device != self.device:
+                        net._packed = torch.empty((self.lib.nerf_mlp_bf16_packed_bytes(),), device=self.device, dtype=torch.uint8)
+                self._call("nerf_train_prologue", _lib.pointer_array([p.detach() for p in c.ordered_parameters()]),
+                           P(c._packed, torch.uint8), _lib.pointer_array([p.detach() for p in f.ordered_parameters()]),
+                           P(f._packed, torch.uint8), P(flat.grad), flat.grad.numel(), P(losses), 2, st)
+                for net in self.nets:
+                    net._packed_version = None  # packed outside NeRF.packed_weights' version tracking
+                self._prologue_done = True
+            else:
+                losses.zero_()
+            try:
+                if uniforms is None:
+                    # one draw for the four tensors of the reference's order (u_c | u0 | u1 | u2), each contiguous
+                    sc, sf = self.sc, self.sf
+                    u_all = torch.rand((n * (2 * sc + 2 * sf),), device=self.device)
+                    o1, o2, o3 = n * sc, 2 * n * sc, 2 * n * sc + n * sf
+                    uc = [u_all[:o1].view(n, sc)]
+                    uf = [u_all[o1:o2].view(n, sc), u_all[o2:o3].view(n, sf), u_all[o3:].view(n, sf)]
+                else:
+                    uc = self._uniforms(n, uniforms[:1], fine=False)
+                    uf = self._uniforms(n, uniforms[1:], fine=True)
+                co = self._pass(0, "c", ray_o, ray_d, n, near, far, None, uc, train=True)
+                # the fine pass perturbs the coarse weights in place (utils.py:31); nothing reads them afterwards (the
+                # compositing backward recomputes the weights), so no private copy is made here
+                fi = self._pass(1, "f", ray_o, ray_d, n, near, far, co["w"], uf, train=True)
+                # autograd order: the fine pass is differentiated first (train.py:190-215)
+                self._backward(1, fi, n, None, flat.grads_of(1), target=target, loss=losses[1:2])
+                self._backward(0, co, n, None, flat.grads_of(0), target=target, loss=losses[0:1])
+            finally:
+                self._prologue_done = False
         self.last = {"coarse": co, "fine": fi}
         return losses
 
