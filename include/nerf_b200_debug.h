@@ -34,6 +34,11 @@ int nerf_debug_set_profile_buffer(unsigned long long* buf_dev, int tiles);
  * 5/6 tiles of the first / second segment.  Pass NULL to switch it off. */
 int nerf_debug_set_wgrad_profile(unsigned long long* buf_dev);
 
+/* timing experiment (the gradients of such a launch are unusable): the next wgrad launches read the gradient tile images of
+ * tile (t % wrap_g) and the activation tile images of tile (t % wrap_x) instead of tile t, i.e. from an L2-resident window --
+ * what the kernel would run at if a producer kept that operand in L2.  0 switches a wrap off. */
+int nerf_debug_set_wgrad_wrap(int64_t wrap_g, int64_t wrap_x);
+
 /* self test + rate probe of the CTA-pair MMA (tcgen05 cta_group::2, M = 256): a (256 x k), b (n x k) bf16 bits, d (256 x n)
  * fp32, all row-major; bit 0 of ts puts the A operand in tensor memory.  `pairs` clusters of two CTAs all compute the same
  * product; with iters > 0 each leader then times iters x (k/16) MMAs into cycles_dev[pair].  With bit 1 of ts (n <= 128,

@@ -391,6 +391,7 @@ struct WgradArgs {
   ParamPtrs grads;
   int64_t m;
   int64_t tile0, tile1;      // this launch covers tiles [tile0, tile1) of the m rows
+  int64_t wrap_g, wrap_x;    // timing experiment only (results unusable): read G / X of tile (t % wrap) instead of t; 0 = off
   unsigned long long* prof;  // optional per-CTA timeline (nerf_debug_set_wgrad_profile): 8 values per CTA
 };
 
@@ -553,8 +554,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(WgradArgs a) {
       const long long ld_t0 = a.prof ? clock64() : 0;
       const uint8_t* ghead = a.scratch + scratch_ghead_offset(a.m);
       for (int64_t tile = tile0; tile < tile1; ++tile) {
-        const uint8_t* gtile = a.scratch + (size_t)tile * kGradTileBytes;
-        const uint8_t* xtile = a.cache + (size_t)tile * kCacheTileBytes;
+        const uint8_t* gtile = a.scratch + (size_t)(a.wrap_g ? tile % a.wrap_g : tile) * kGradTileBytes;
+        const uint8_t* xtile = a.cache + (size_t)(a.wrap_x ? tile % a.wrap_x : tile) * kCacheTileBytes;
         for (int sl = 0; sl < 4; ++sl) {
           const uint32_t ph = (phase_bits >> s) & 1u;
           const long long w0 = a.prof ? clock64() : 0;
@@ -778,6 +779,7 @@ __global__ void zero_grads_kernel(ParamPtrs g) {
 }
 
 static unsigned long long* g_wgrad_prof = nullptr;
+static int64_t g_wgrad_wrap_g = 0, g_wgrad_wrap_x = 0;
 
 // Per-device one-time setup (shared-memory opt-in of the kernels, the wgrad unit table in constant memory).  A process
 // that drives several GPUs must do this on each of them, hence the per-device flags.
@@ -833,6 +835,7 @@ static int launch_backward(const void* packed_dev, const void* cache_dev, const 
     a.grads = gp;
     a.m = m;
     a.tile0 = tile0, a.tile1 = tile1;
+    a.wrap_g = g_wgrad_wrap_g, a.wrap_x = g_wgrad_wrap_x;
     a.prof = g_wgrad_prof;
     mlp_wgrad_kernel<<<sms, kWgThreads, kWgSmemBytes, st>>>(a);
     NERF_LAUNCH_CHECK();
@@ -846,6 +849,11 @@ using namespace nerf;
 
 extern "C" int nerf_debug_set_wgrad_profile(unsigned long long* buf_dev) {
   g_wgrad_prof = buf_dev;
+  return NERF_OK;
+}
+
+extern "C" int nerf_debug_set_wgrad_wrap(int64_t wrap_g, int64_t wrap_x) {
+  g_wgrad_wrap_g = wrap_g, g_wgrad_wrap_x = wrap_x;
   return NERF_OK;
 }
 
