@@ -781,6 +781,22 @@ def run_b200(args):
             except Exception as err:
                 dropin = {"unavailable": f"{type(err).__name__}: {err}"[:300]}
         step_flop = n_rays * (SC + SC + SF) * FLOP_TRAIN_PER_EVAL
+        # the whole step against both roofs: its tensor work against the sustained bf16 peak, and the HBM bytes its three
+        # tensor-core kernel families move (ncu dram bytes of the fine pass's launches, recorded in profiles/traffic.json,
+        # x 4/3 for the coarse pass) against the copy bandwidth -- the design stages activations and activation
+        # gradients in HBM, so the step sits between the two roofs
+        roof_step = None
+        if args.precision == "bf16":
+            m_f = n_rays * (SC + SF)
+            tr = [recorded_traffic(k, m_f) for k in ("mlp_fwd_kernel<1>", "mlp_dgrad_kernel", "mlp_wgrad_kernel")]
+            hbm_bytes = None if any(t is None for t in tr) else sum(tr) * (SC + SC + SF) / (SC + SF)
+            sec_step = ms_dev / args.steps * 1e-3
+            roof_step = {"tensor": {"achieved": step_flop / sec_step / 1e12, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                                    "frac": step_flop / sec_step / 1e12 / pk["tf_sustained"]},
+                         "hbm": None if hbm_bytes is None else
+                         {"achieved": hbm_bytes / sec_step / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                          "frac": hbm_bytes / sec_step / 1e9 / pk["hbm_gbs"], "traffic": hbm_bytes},
+                         "peak_source": pk["src"] + " (sustained: kernels timed inside the step)"}
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong" if args.global_rays else "weak",
@@ -798,7 +814,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks,
             "step_tensor_frac_sustained": step_flop / (ms_dev / args.steps * 1e-3) / 1e12 / pk["tf_sustained"],
-            "roofline": roof, "roofline_mlp": roof_mlp, "roofline_stages": stages, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "dropin": dropin, "dp_parity": parity,
+            "roofline": roof, "roofline_mlp": roof_mlp, "roofline_step": roof_step, "roofline_stages": stages, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "dropin": dropin, "dp_parity": parity,
             "c4_global_32768": c4,
             "render": render,
             "loss_last": [float(x) for x in losses_host[total_steps - 1]],

@@ -370,7 +370,7 @@ struct BlkLayout {
   __device__ static __forceinline__ int pos3(int f) { return f + f / (3 * G); }
 };
 
-template <int G, int MB>
+template <int G, int MB, bool kMse>
 __global__ void __launch_bounds__(kCompWarps * 32, MB)
     composite_bwd_blk_kernel(const float* __restrict__ sigma, const float* __restrict__ radiance,
                              const float* __restrict__ delta, const float* __restrict__ g_rgb,
@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(kCompWarps * 32, MB)
     // g_rgb is either given, or (training step) `g_rgb` holds the rendered colour and the MSE head is folded in here:
     // g = 2/(3N) (rgb - target), loss += mean((rgb - target)^2)   (runner_utils.py:731, train.py:180/202)
     float gr = __ldg(g_rgb + 3 * ray), gg = __ldg(g_rgb + 3 * ray + 1), gb = __ldg(g_rgb + 3 * ray + 2);
-    if (mse_target != nullptr) {
+    if (kMse) {
       const float dr = gr - __ldg(mse_target + 3 * ray), dg = gg - __ldg(mse_target + 3 * ray + 1),
                   db = gb - __ldg(mse_target + 3 * ray + 2);
       gr = 2.0f * inv_cnt * dr, gg = 2.0f * inv_cnt * dg, gb = 2.0f * inv_cnt * db;
@@ -524,8 +524,12 @@ static void launch_composite_bwd_blk(const float* sigma, const float* radiance, 
   // 866 us at 80, 875 us at 64 (640 000 rays)
   // CTAs per SM measured on 192 samples (640 000 rays): 5 -> 778 us, 6 -> 768 us, 7 (72 registers) -> 704 us, 8 -> 797 us
   constexpr int kMinBlocks = G <= 6 ? 7 : 4;
-  composite_bwd_blk_kernel<G, kMinBlocks><<<(unsigned)ceil_div64(n, kCompWarps), kCompWarps * 32, 0, stream>>>(
-      sigma, radiance, delta, g_rgb, g_w, n, s, g_sigma, g_radiance, mse_target, inv_cnt, loss_accum);
+  if (mse_target != nullptr)
+    composite_bwd_blk_kernel<G, kMinBlocks, true><<<(unsigned)ceil_div64(n, kCompWarps), kCompWarps * 32, 0, stream>>>(
+        sigma, radiance, delta, g_rgb, g_w, n, s, g_sigma, g_radiance, mse_target, inv_cnt, loss_accum);
+  else
+    composite_bwd_blk_kernel<G, kMinBlocks, false><<<(unsigned)ceil_div64(n, kCompWarps), kCompWarps * 32, 0, stream>>>(
+        sigma, radiance, delta, g_rgb, g_w, n, s, g_sigma, g_radiance, nullptr, 0.f, nullptr);
 }
 
 }  // namespace nerf
