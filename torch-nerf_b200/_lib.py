@@ -13,8 +13,10 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libnerf_b200.so")
-SELFTEST_LIB_PATH = os.path.join(_PKG, "lib", "libnerf_b200_selftest.so")
+# NERF_B200_LIB_SUFFIX selects an experimental build made by build.py with the same variable (kernel variants under test)
+_SUFFIX = os.environ.get("NERF_B200_LIB_SUFFIX", "")
+LIB_PATH = os.path.join(_PKG, "lib", f"libnerf_b200{_SUFFIX}.so")
+SELFTEST_LIB_PATH = os.path.join(_PKG, "lib", f"libnerf_b200{_SUFFIX}_selftest.so")
 
 NERF_OK, NERF_ERR_ARG, NERF_ERR_CUDA = 0, 1, 2
 NUM_PARAM_TENSORS = 22

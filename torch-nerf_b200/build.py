@@ -15,15 +15,17 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
-LIB = os.path.join(LIB_DIR, "libnerf_b200.so")
-LIB_SELFTEST = os.path.join(LIB_DIR, "libnerf_b200_selftest.so")
+# experiments: NERF_B200_LIB_SUFFIX=_x NERF_B200_NVCC_EXTRA="-DFOO=1" builds lib/libnerf_b200_x.so next to the product library
+_SUFFIX = os.environ.get("NERF_B200_LIB_SUFFIX", "")
+LIB = os.path.join(LIB_DIR, f"libnerf_b200{_SUFFIX}.so")
+LIB_SELFTEST = os.path.join(LIB_DIR, f"libnerf_b200{_SUFFIX}_selftest.so")
 SOURCES = ["api.cu", "rays.cu", "encode_composite.cu", "mlp_f32.cu", "mlp_tc_pack.cu", "mlp_tc_fwd.cu", "mlp_tc_bwd.cu",
            "optim.cu", "dp_exchange.cu"]
 SELFTEST_SOURCES = ["mlp_tc_selftest.cu"]  # links against libnerf_b200.so (error string, SM count)
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
-]
+] + os.environ.get("NERF_B200_NVCC_EXTRA", "").split()
 
 
 def _nvcc():
@@ -46,13 +48,13 @@ def _digest():
 
 def build(force: bool = False, verbose: bool = True) -> str:
     os.makedirs(LIB_DIR, exist_ok=True)
-    stamp = os.path.join(LIB_DIR, "build.sha256")
+    stamp = os.path.join(LIB_DIR, f"build{_SUFFIX}.sha256")
     digest = _digest()
     if (not force and os.path.exists(LIB) and os.path.exists(LIB_SELFTEST) and os.path.exists(stamp)
             and open(stamp).read().strip() == digest):
         return LIB
     nvcc = _nvcc()
-    obj_dir = os.path.join(ROOT, "build", "obj")
+    obj_dir = os.path.join(ROOT, "build", "obj" + _SUFFIX)
     os.makedirs(obj_dir, exist_ok=True)
     procs = []
     for src in SOURCES + SELFTEST_SOURCES:
@@ -69,7 +71,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
         (st_objs if src in SELFTEST_SOURCES else objs).append(obj)
     link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
     for cmd in ([*link, "-o", LIB, *objs],
-                [*link, "-o", LIB_SELFTEST, *st_objs, "-L" + LIB_DIR, "-lnerf_b200", "-Xlinker", "-rpath=$ORIGIN"]):
+                [*link, "-o", LIB_SELFTEST, *st_objs, "-L" + LIB_DIR, "-lnerf_b200" + _SUFFIX, "-Xlinker", "-rpath=$ORIGIN"]):
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}")

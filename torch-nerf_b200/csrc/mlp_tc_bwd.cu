@@ -153,10 +153,10 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
         const int nk = bwd_nk(j);
         for (int h = 0; h < 2; ++h) {
           if (h == 0) {  // the layer's G operand is in TMEM (and the accumulator has been drained)
-            mbar_wait(&a_ready[slot], n_a & 1);
+            issuer_wait(&a_ready[slot], n_a & 1);
             ++n_a;
           } else {       // N-half 0 is out of the accumulator
-            mbar_wait(&acc_free[slot], n_free & 1);
+            issuer_wait(&acc_free[slot], n_free & 1);
             ++n_free;
           }
 #pragma unroll 1
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
         uint8_t* gblk0 = g_tile + grad_slice_off(2 + 4 * j + blk, q);  // gradient block of N-half 0's columns
         // ---- N-half 0: pull it out of the accumulator first (the issuer is waiting for that), then convert and hold it
         {
-          mbar_wait(&acc_full[slot], n_full & 1);
+          epilogue_wait(&acc_full[slot], n_full & 1);
           ++n_full;
           tc_fence_after();
           uint32_t v0[32], v1[32];
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) mlp_dgrad_kernel(DgradArgs a) {
         // ---- N-half 1: once complete nothing reads the G operand any more -> overwrite it in place, signal the
         //      issuer, then store the gradient block for wgrad
         {
-          mbar_wait(&acc_full[slot], n_full & 1);
+          epilogue_wait(&acc_full[slot], n_full & 1);
           ++n_full;
           tc_fence_after();
           uint32_t v[32], w0[16], w1[16];

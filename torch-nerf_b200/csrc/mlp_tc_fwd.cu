@@ -296,11 +296,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
             const long long w0 = stamp ? clock64() : 0;
             if (h == 0) {
               if (l >= 1) {  // the epilogue has rewritten this slot's layer input (and drained the accumulator)
-                mbar_wait(&a_ready[slot], n_a & 1);
+                issuer_wait(&a_ready[slot], n_a & 1);
                 ++n_a;
               }
             } else {         // N-half 0 is out of the accumulator
-              mbar_wait(&acc_free[slot], n_free & 1);
+              issuer_wait(&acc_free[slot], n_free & 1);
               ++n_free;
             }
             if (stamp) wait_a += clock64() - w0;
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
         const int cblk0 = (l < 8 ? cache_h(l) : kCacheFeat) + blk;  // cache block of N-half 0's columns
         // ---- N-half 0: pull it out of the accumulator first (the issuer is waiting for that), then convert and hold it
         {
-          mbar_wait(&acc_full[slot], n_full & 1);
+          epilogue_wait(&acc_full[slot], n_full & 1);
           ++n_full;
           tc_fence_after();
           if (stamp) a.prof[((iter * kNumFwdLayers + l) * 8) + 2] = clock64();
@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
         // ---- N-half 1: once it is complete nothing reads the layer input any more -> overwrite it in place, signal
         //      the issuer, and only then do the training-cache stores
         {
-          mbar_wait(&acc_full[slot], n_full & 1);
+          epilogue_wait(&acc_full[slot], n_full & 1);
           ++n_full;
           tc_fence_after();
           uint32_t v[32], w0[16], w1[16];
@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(FwdArgs a) {
       // ---- fc_9 output (128 columns = one N-half): this warp owns columns [64 blk, 64 blk + 64)
       {
         const int l = kNumFwdLayers - 1;
-        mbar_wait(&acc_full[slot], n_full & 1);
+        epilogue_wait(&acc_full[slot], n_full & 1);
         ++n_full;
         tc_fence_after();
         if (stamp) a.prof[((iter * kNumFwdLayers + l) * 8) + 2] = clock64();

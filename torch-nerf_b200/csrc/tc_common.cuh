@@ -81,6 +81,24 @@ __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Hand-over waits of the chain kernels (accumulator full -> epilogue, operand ready / accumulator free -> issuer).
+// try_wait may park the warp; test_wait spins on the issue slot.  Which is faster is a measurement:
+// compile with -DNERF_SPIN_ISSUER=1 / -DNERF_SPIN_EPI=1 to spin.
+#ifndef NERF_SPIN_ISSUER
+#define NERF_SPIN_ISSUER 0
+#endif
+#ifndef NERF_SPIN_EPI
+#define NERF_SPIN_EPI 0
+#endif
+__device__ __forceinline__ void issuer_wait(uint64_t* bar, uint32_t parity) {
+  if (NERF_SPIN_ISSUER) mbar_wait_spin(bar, parity);
+  else mbar_wait(bar, parity);
+}
+__device__ __forceinline__ void epilogue_wait(uint64_t* bar, uint32_t parity) {
+  if (NERF_SPIN_EPI) mbar_wait_spin(bar, parity);
+  else mbar_wait(bar, parity);
+}
+
 // ---------------------------------------------------------------- bulk async copies (TMA engine, 1-D)
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
