@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def tn():
     import torch_nerf_b200 as mod
 
-    if not os.path.exists(mod._lib.LIB_PATH):
+    if not (os.path.exists(mod._lib.LIB_PATH) and os.path.exists(mod._lib.SELFTEST_LIB_PATH)):
         import importlib.util
 
         spec = importlib.util.spec_from_file_location("nerf_build", os.path.join(ROOT, "torch-nerf_b200", "build.py"))

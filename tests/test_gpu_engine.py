@@ -287,3 +287,21 @@ def test_engine_graph_replay_matches_eager(tn):
         torch.testing.assert_close(rg, re, rtol=0, atol=2e-2)
         cos = torch.nn.functional.cosine_similarity(gg, ge, dim=0)
         assert float(cos) > 0.995, (i, float(cos))
+
+
+def test_engine_depth_and_opacity_outputs(tn):
+    """North-star outputs without a reference counterpart: depth = sum_i w_i t_i, opacity = sum_i w_i of
+    the fine pass, checked against those definitions on the engine's own weights and sample distances."""
+    from torch_nerf_b200.engine import HotPathEngine
+
+    g = load_golden("render.npz")
+    coarse, fine = nets(tn, int(g["seed_c"]), int(g["seed_f"]), "bf16")
+    eng = HotPathEngine(coarse, fine, 64, 128, precision="bf16")
+    cam = camera(tn, g)
+    ray_o, ray_d, n = eng.rays_from_pixels(cam, False, None, 0, int(g["h"]) * int(g["w"]))
+    out = eng.render_rays(ray_o, ray_d, 2.0, 6.0, uniforms=(cu(g["u_c"]), cu(g["u0"]), cu(g["u1"]), cu(g["u2"])), want_depth=True)
+    torch.cuda.synchronize()
+    w, t = out["weights_fine"].double(), out["t_fine"].double()
+    torch.testing.assert_close(out["depth_fine"].double(), (w * t).sum(-1), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(out["opacity_fine"].double(), w.sum(-1), rtol=1e-5, atol=1e-5)
+    assert float(out["opacity_fine"].max()) <= 1.0 + 1e-5 and float(out["depth_fine"].min()) >= 0.0

@@ -146,8 +146,9 @@ class HotPathEngine:
                        P(u[2]), None, P(t), P(pts), P(dirs), P(delta), st)
         return t, delta, pts, dirs, s
 
-    def _pass(self, which: int, tag: str, ray_o, ray_d, n, near, far, weights, u, train: bool):
-        """One render pass (coarse: which=0, fine: which=1): sample -> query -> composite."""
+    def _pass(self, which: int, tag: str, ray_o, ray_d, n, near, far, weights, u, train: bool, want_depth: bool = False):
+        """One render pass (coarse: which=0, fine: which=1): sample -> query -> composite.  `want_depth` also produces
+        depth = sum_i w_i t_i and opacity = sum_i w_i (north-star outputs without a reference counterpart)."""
         P, st = _lib.ptr, _lib.stream()
         net = self.nets[which]
         fp32 = self.precision == "fp32"
@@ -180,8 +181,11 @@ class HotPathEngine:
                        P(rad), P(cache, torch.uint8) if cache is not None else None, st)
         rgb = self._get(tag + "rgb", (n, 3))
         w = self._get(tag + "w", (n, s))
-        self._call("nerf_composite_fwd", P(sigma), P(rad), P(delta), None, n, s, P(rgb), P(w), None, None, st)
-        ctx["rgb"], ctx["w"] = rgb, w
+        depth = self._get(tag + "depth", (n,)) if want_depth else None
+        opacity = self._get(tag + "opacity", (n,)) if want_depth else None
+        self._call("nerf_composite_fwd", P(sigma), P(rad), P(delta), P(t) if want_depth else None, n, s, P(rgb), P(w), P(depth),
+                   P(opacity), st)
+        ctx["rgb"], ctx["w"], ctx["depth"], ctx["opacity"] = rgb, w, depth, opacity
         return ctx
 
     def _backward(self, which: int, ctx, n: int, g_rgb, grads, target=None, loss=None):
@@ -230,8 +234,9 @@ class HotPathEngine:
         return ray_o, ray_d, n
 
     @torch.no_grad()
-    def render_rays(self, ray_o, ray_d, near: float, far: float, uniforms=None):
-        """Coarse + fine forward for given rays.  uniforms = (u_c, u0, u1, u2) or None."""
+    def render_rays(self, ray_o, ray_d, near: float, far: float, uniforms=None, want_depth: bool = False):
+        """Coarse + fine forward for given rays.  uniforms = (u_c, u0, u1, u2) or None.  `want_depth` adds the fine pass's
+        per-ray depth and opacity to the result."""
         n = ray_o.shape[0]
         with torch.cuda.device(self.device):
             uc = self._uniforms(n, None if uniforms is None else uniforms[:1], fine=False)
@@ -241,10 +246,13 @@ class HotPathEngine:
             # weights stay as rendered
             w_pdf = self._get("w_pdf", (n, self.sc))
             w_pdf.copy_(co["w"])
-            fi = self._pass(1, "f", ray_o, ray_d, n, float(near), float(far), w_pdf, uf, train=False)
+            fi = self._pass(1, "f", ray_o, ray_d, n, float(near), float(far), w_pdf, uf, train=False, want_depth=want_depth)
         self.last = {"coarse": co, "fine": fi}
-        return {"rgb_coarse": co["rgb"], "weights_coarse": co["w"], "rgb_fine": fi["rgb"], "weights_fine": fi["w"],
-                "t_fine": fi["t"]}
+        out = {"rgb_coarse": co["rgb"], "weights_coarse": co["w"], "rgb_fine": fi["rgb"], "weights_fine": fi["w"],
+               "t_fine": fi["t"]}
+        if want_depth:
+            out["depth_fine"], out["opacity_fine"] = fi["depth"], fi["opacity"]
+        return out
 
     @torch.no_grad()
     def render_frame(self, camera: PerspectiveCamera, project_to_ndc: bool = False, first_pixel: int = 0,
