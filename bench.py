@@ -344,10 +344,10 @@ def dropin_block(tn, dev, n_rays, eng_render):
         gt = torch.rand(IMG * IMG, 3)
         dev_i = dev.index if dev.index is not None else torch.cuda.current_device()
 
-        def step():
+        def step(pix=None):
             opt.zero_grad()
             ren.camera = tn.PerspectiveCamera(intr, c2w, 2.0, 6.0)
-            pred_c, idx, w_c = ren.render_scene(scenes[0], n_rays, SC, False, dev_i)
+            pred_c, idx, w_c = ren.render_scene(scenes[0], n_rays, SC, False, dev_i, pixel_indices=pix)
             loss = loss_fn(gt[idx].to(dev), pred_c)
             pred_f, idx_f, _ = ren.render_scene(scenes[1], n_rays, (SC, SF), False, dev_i, pixel_indices=idx, weights=w_c)
             loss = loss + loss_fn(gt[idx_f].to(dev), pred_f)
@@ -367,6 +367,26 @@ def dropin_block(tn, dev, n_rays, eng_render):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
         out[f"train_{precision}"] = {"rays_per_step": n_rays, "ms_per_step": ms, "rays_per_s": n_rays / (ms * 1e-3), "steps": steps}
+        if precision == "bf16":
+            # the same step with the pixel batch GIVEN (train.py:150-169 passes pixel_indices during its warm-up epochs):
+            # without the reference's host-side np.random.choice(H*W, n, replace=False) of volume_renderer.py:122-128, which
+            # this package mirrors and which alone costs ~6-10 ms of host time per pass at 800x800
+            gpix = torch.Generator().manual_seed(5)
+            pixs = [torch.randperm(IMG * IMG, generator=gpix)[:n_rays] for _ in range(steps + 2)]
+            for i in range(2):
+                step(pixs[i])
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(steps):
+                step(pixs[2 + i])
+            e1.record()
+            torch.cuda.synchronize()
+            ms_p = e0.elapsed_time(e1) / steps
+            t_c = time.perf_counter()
+            for _ in range(3):
+                np.random.choice(IMG * IMG, size=[n_rays], replace=False)
+            out["train_bf16_pixels_given"] = {"rays_per_step": n_rays, "ms_per_step": ms_p, "rays_per_s": n_rays / (ms_p * 1e-3),
+                                              "steps": steps, "host_np_random_choice_ms": (time.perf_counter() - t_c) / 3 * 1e3}
         # config C1: 100x100 frame, num_ray_batch = 10000 // 4096 = 2 (render.py:81-99)
         intr1, c2w1 = _ref_scene(100)
         ren.camera = tn.PerspectiveCamera(intr1, c2w1, 2.0, 6.0)
