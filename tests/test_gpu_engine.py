@@ -305,3 +305,58 @@ def test_engine_depth_and_opacity_outputs(tn):
     torch.testing.assert_close(out["depth_fine"].double(), (w * t).sum(-1), rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(out["opacity_fine"].double(), w.sum(-1), rtol=1e-5, atol=1e-5)
     assert float(out["opacity_fine"].max()) <= 1.0 + 1e-5 and float(out["depth_fine"].min()) >= 0.0
+
+
+@pytest.mark.parametrize("n", [1, 129, 1001])
+def test_engine_ragged_ray_counts(tn, n):
+    """Ray counts that are not multiples of anything (1 ray = 64 / 192 rows, a partial 128-row tile; odd tile counts so the
+    chain kernels' second tile slot runs empty): the bf16 iteration must match the fp32-validation iteration on the same
+    pixels and uniforms, and the render must match the oracle."""
+    from torch_nerf_b200.engine import HotPathEngine
+
+    g = load_golden("train_step.npz")
+    cam = camera(tn, g)
+    gen = torch.Generator().manual_seed(n)
+    pix = torch.randperm(int(g["h"]) * int(g["w"]), generator=gen)[:n].cuda() if n <= int(g["h"]) * int(g["w"]) else None
+    if pix is None:
+        pix = torch.randint(0, int(g["h"]) * int(g["w"]), (n,), generator=gen).cuda()
+    tgt = torch.rand((n, 3), generator=gen).cuda()
+    u = tuple(torch.rand((n, k), generator=gen).cuda() for k in (64, 64, 128, 128))
+    grads = {}
+    for precision in ("fp32", "bf16"):
+        coarse, fine = nets(tn, 61, 62, precision)
+        eng = HotPathEngine(coarse, fine, 64, 128, precision=precision)
+        losses = eng.train_pixels(cam, pix, tgt, False, uniforms=u)
+        torch.cuda.synchronize()
+        assert torch.isfinite(losses).all()
+        grads[precision] = (eng.flat.grad.clone(), losses.clone(), eng.last["coarse"]["rgb"].clone())
+    g32, g16 = grads["fp32"][0].double(), grads["bf16"][0].double()
+    assert torch.isfinite(g16).all()
+    half = g32.numel() // 2
+    cos_c = float(torch.dot(g32[:half], g16[:half]) / (g32[:half].norm() * g16[:half].norm() + 1e-30))
+    assert cos_c > 0.97, cos_c                     # coarse network: same samples in both precisions
+    np.testing.assert_allclose(grads["bf16"][1][0].item(), grads["fp32"][1][0].item(), rtol=3e-2)
+    np.testing.assert_allclose(grads["bf16"][2].cpu().numpy(), grads["fp32"][2].cpu().numpy(), rtol=0, atol=3e-2)
+    # coarse render against the oracle
+    ray_o, ray_d, _ = eng.rays_from_pixels(cam, False, pix)
+    co = orc.render_pass(orc.init_nerf_params(seed=61), ray_o.cpu().numpy(), ray_d.cpu().numpy(), 2.0, 6.0, 64, (u[0].cpu().numpy(),))
+    np.testing.assert_allclose(grads["fp32"][2].cpu().numpy(), co["rgb"], rtol=0, atol=1e-3)
+
+
+def test_empty_inputs_are_accepted(tn):
+    """n = 0 everywhere: zero-size tensors (null data pointers) must be no-ops, like the reference's tensor ops."""
+    lib, P, st = tn._lib.load(), tn._lib.ptr, tn._lib.stream
+    e = lambda *shape: torch.empty(shape, device="cuda")
+    ck = tn._lib.check
+    ck(lib.nerf_sample_coarse(P(e(0, 3)), P(e(0, 3)), 0, 64, 2.0, 6.0, P(e(0, 64)), P(e(0, 64)), None, None, P(e(0, 64)), st()), "coarse")
+    ck(lib.nerf_sample_fine(P(e(0, 3)), P(e(0, 3)), 0, 64, 128, 2.0, 6.0, P(e(0, 64)), P(e(0, 64)), P(e(0, 128)), P(e(0, 128)), None,
+                            P(e(0, 192)), None, None, P(e(0, 192)), st()), "fine")
+    ck(lib.nerf_composite_fwd(P(e(0, 64)), P(e(0, 64, 3)), P(e(0, 64)), None, 0, 64, P(e(0, 3)), P(e(0, 64)), None, None, st()), "cf")
+    ck(lib.nerf_composite_bwd(P(e(0, 64)), P(e(0, 64, 3)), P(e(0, 64)), P(e(0, 3)), None, 0, 64, P(e(0, 64)), P(e(0, 64, 3)), st()), "cb")
+    ck(lib.nerf_posenc(P(e(0, 3)), 0, 3, 10, 1, P(e(0, 63)), 63, st()), "pe")
+    packed = tn.NeRF(63, 27, precision="bf16").cuda().packed_weights(True)
+    ck(lib.nerf_mlp_bf16_forward(P(packed, torch.uint8), None, None, P(e(0, 3)), P(e(0, 3)), P(e(0, 64)), 64, 0, P(e(0)), P(e(0, 3)), None,
+                                 st()), "mlp")
+    torch.cuda.synchronize()
+    q = tn.QuadratureIntegrator().integrate_along_rays(e(0, 64), e(0, 64, 3), e(0, 64))
+    assert q[0].shape == (0, 3) and q[1].shape == (0, 64)
