@@ -77,6 +77,11 @@ int nerf_generate_rays_from_pixels_devcam(const int64_t* pixel_idx_dev, int64_t 
                                           const nerf_camera_t* cam_dev, float* ray_o_dev, float* ray_d_dev,
                                           nerf_stream_t stream);
 
+/* RaySamplerBase.map_rays_to_ndc (sampler_base.py:199-257) on its own: projects world-frame rays (N,3) to NDC;
+ * out_* may alias the inputs.  (nerf_generate_rays* apply the same projection when camera.project_to_ndc is set.) */
+int nerf_map_rays_to_ndc(const float* ray_o_dev, const float* ray_d_dev, int64_t n, double focal_length, double z_near,
+                         int img_height, int img_width, float* out_o_dev, float* out_d_dev, nerf_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K2 / K3 sampling along rays
  *   replaces StratifiedSampler.sample_along_rays (src/renderer/ray_samplers/stratified_sampler.py:17-128)

@@ -404,3 +404,20 @@ def test_train_step_golden_fp32(tn):
     np.testing.assert_allclose(loss_f.item(), float(g["loss_f"]), rtol=1e-3)
     check_digest({k: p.grad.cpu().numpy() for k, p in net_c.named_parameters()}, g, prefix="c/", rtol=5e-3, atol=1e-6)
     check_digest({k: p.grad.cpu().numpy() for k, p in net_f.named_parameters()}, g, prefix="f/", rtol=5e-3, atol=1e-6)
+
+
+@pytest.mark.parametrize("near", [0.0, 1.0])
+def test_map_rays_to_ndc_standalone(tn, near):
+    """RaySamplerBase.map_rays_to_ndc (sampler_base.py:199-257) on its own against the oracle's restatement."""
+    rng = np.random.default_rng(3)
+    n = 5000
+    o = rng.normal(size=(n, 3)).astype(np.float32)
+    o[:, 2] = np.abs(o[:, 2]) + 0.5
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d[:, 2] = -np.abs(d[:, 2]) - 0.1
+    ro, rd = orc.map_rays_to_ndc(815.0, near, 756, 1008, o, d)
+    po, pd = tn.StratifiedSampler().map_rays_to_ndc(815.0, near, 756, 1008, torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda())
+    np.testing.assert_allclose(po.cpu().numpy(), ro, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(pd.cpu().numpy(), rd, rtol=1e-6, atol=1e-6)
+    with pytest.raises(ValueError):
+        tn.StratifiedSampler().map_rays_to_ndc(815.0, -1.0, 756, 1008, torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda())

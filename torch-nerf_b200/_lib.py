@@ -47,6 +47,7 @@ _PROTOTYPES = {
     "nerf_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "nerf_generate_rays": (c_int, [_P, c_int64, POINTER(CameraStruct), _P, _P, _P]),
     "nerf_generate_rays_from_pixels": (c_int, [_P, c_int64, c_int64, POINTER(CameraStruct), _P, _P, _P]),
+    "nerf_map_rays_to_ndc": (c_int, [_P, _P, c_int64, c_double, c_double, c_int, c_int, _P, _P, _P]),
     "nerf_upload_camera": (c_int, [_P, POINTER(CameraStruct), _P]),
     "nerf_generate_rays_from_pixels_devcam": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P]),
     "nerf_make_bins": (c_int, [c_double, c_double, c_int, POINTER(c_float), POINTER(c_float)]),

@@ -22,6 +22,33 @@ namespace nerf {
 // kRPT rays per thread: 4 rays = 12 floats = three 16-byte stores per output (frame-sized launches); small training
 // batches use one ray per thread so that a 4096-ray launch still fills more than a handful of warps
 
+// sampler_base.py:236-255 (map_rays_to_ndc): sx = -(2 f / W), sy = -(2 f / H), two_near = 2 z_near; in place
+__device__ __forceinline__ void ndc_project(float sx, float sy, float two_near, float* o, float* d) {
+  float oxz = __fdiv_rn(o[0], o[2]);
+  float oyz = __fdiv_rn(o[1], o[2]);
+  float nz = __fdiv_rn(two_near, o[2]);
+  float no0 = __fmul_rn(sx, oxz);
+  float no1 = __fmul_rn(sy, oyz);
+  float no2 = __fadd_rn(1.0f, nz);
+  float nd0 = __fmul_rn(sx, __fsub_rn(__fdiv_rn(d[0], d[2]), oxz));
+  float nd1 = __fmul_rn(sy, __fsub_rn(__fdiv_rn(d[1], d[2]), oyz));
+  float nd2 = -nz;
+  o[0] = no0, o[1] = no1, o[2] = no2;
+  d[0] = nd0, d[1] = nd1, d[2] = nd2;
+}
+
+__global__ void __launch_bounds__(256) ndc_kernel(const float* __restrict__ ray_o, const float* __restrict__ ray_d, int64_t n,
+                                                   float sx, float sy, float two_near, float* __restrict__ out_o,
+                                                   float* __restrict__ out_d) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float o[3] = {ray_o[3 * i], ray_o[3 * i + 1], ray_o[3 * i + 2]};
+  float d[3] = {ray_d[3 * i], ray_d[3 * i + 1], ray_d[3 * i + 2]};
+  ndc_project(sx, sy, two_near, o, d);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) out_o[3 * i + j] = o[j], out_d[3 * i + j] = d[j];
+}
+
 __device__ __forceinline__ void one_ray(const int64_t* __restrict__ coords, const int64_t* __restrict__ pix,
                                         int64_t first_pixel, int64_t i, const nerf_camera_t& cam, float* o, float* d) {
   float u, v;
@@ -53,20 +80,7 @@ __device__ __forceinline__ void one_ray(const int64_t* __restrict__ coords, cons
     d[j] = acc;
     o[j] = cam.trans[j];  // sampler_base.py:165
   }
-  if (cam.project_to_ndc) {
-    // sampler_base.py:236-255
-    float oxz = __fdiv_rn(o[0], o[2]);
-    float oyz = __fdiv_rn(o[1], o[2]);
-    float nz = __fdiv_rn(cam.ndc_two_near, o[2]);
-    float no0 = __fmul_rn(cam.ndc_sx, oxz);
-    float no1 = __fmul_rn(cam.ndc_sy, oyz);
-    float no2 = __fadd_rn(1.0f, nz);
-    float nd0 = __fmul_rn(cam.ndc_sx, __fsub_rn(__fdiv_rn(d[0], d[2]), oxz));
-    float nd1 = __fmul_rn(cam.ndc_sy, __fsub_rn(__fdiv_rn(d[1], d[2]), oyz));
-    float nd2 = -nz;
-    o[0] = no0, o[1] = no1, o[2] = no2;
-    d[0] = nd0, d[1] = nd1, d[2] = nd2;
-  }
+  if (cam.project_to_ndc) ndc_project(cam.ndc_sx, cam.ndc_sy, cam.ndc_two_near, o, d);
 }
 
 // `cam_dev` != null: the camera is read from device memory (a captured CUDA graph replays with whatever camera
@@ -639,6 +653,21 @@ int nerf_generate_rays_from_pixels(const int64_t* pixel_idx_dev, int64_t first_p
   NERF_CHECK_ARG(cam && ray_o_dev && ray_d_dev, "nerf_generate_rays_from_pixels: null pointer");
   NERF_CHECK_ARG(cam->img_w > 0 && cam->img_h > 0, "nerf_generate_rays_from_pixels: bad image size");
   launch_raygen(nullptr, pixel_idx_dev, first_pixel, n, *cam, nullptr, ray_o_dev, ray_d_dev, as_stream(stream));
+  NERF_LAUNCH_CHECK();
+  return NERF_OK;
+}
+
+int nerf_map_rays_to_ndc(const float* ray_o_dev, const float* ray_d_dev, int64_t n, double focal_length, double z_near,
+                         int img_height, int img_width, float* out_o_dev, float* out_d_dev, nerf_stream_t stream) {
+  NERF_CHECK_ARG(n >= 0, "nerf_map_rays_to_ndc: negative ray count");
+  NERF_CHECK_ARG(z_near >= 0, "nerf_map_rays_to_ndc: z_near must be >= 0");
+  NERF_CHECK_ARG(img_height > 0 && img_width > 0, "nerf_map_rays_to_ndc: bad image size");
+  if (n == 0) return NERF_OK;
+  NERF_CHECK_ARG(ray_o_dev && ray_d_dev && out_o_dev && out_d_dev, "nerf_map_rays_to_ndc: null pointer");
+  // the scale factors are Python floats in the reference (evaluated in double, applied as float32 scalars)
+  const float sx = (float)(-(2 * focal_length / img_width)), sy = (float)(-(2 * focal_length / img_height));
+  ndc_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, as_stream(stream)>>>(ray_o_dev, ray_d_dev, n, sx, sy, (float)(2 * z_near),
+                                                                        out_o_dev, out_d_dev);
   NERF_LAUNCH_CHECK();
   return NERF_OK;
 }

@@ -111,6 +111,22 @@ class RaySamplerBase:
             )
         return RayBundle(ray_o, ray_d, t_near=camera.t_near, t_far=camera.t_far, is_ndc=project_to_ndc)
 
+    def map_rays_to_ndc(self, focal_length: float, z_near: float, img_height: int, img_width: int, ray_origin: torch.Tensor,
+                        ray_dir: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """sampler_base.py:199-257: world-frame rays (N,3) -> NDC (no shift of the origin to the near plane, like the
+        reference).  Returns (projected_origin, projected_dir)."""
+        if z_near < 0:
+            raise ValueError(f"Expected a real number greater than or equal to 0. Got {z_near}.")
+        lib = _lib.load()
+        dev = _cuda_device(ray_origin.device if ray_origin.is_cuda else None)
+        o, d = _f32_cuda(ray_origin, dev), _f32_cuda(ray_dir, dev)
+        out_o, out_d = torch.empty_like(o), torch.empty_like(d)
+        with torch.cuda.device(dev):
+            _lib.check(lib.nerf_map_rays_to_ndc(_lib.ptr(o), _lib.ptr(d), o.shape[0], float(focal_length), float(z_near),
+                                                int(img_height), int(img_width), _lib.ptr(out_o), _lib.ptr(out_d), _lib.stream()),
+                       "nerf_map_rays_to_ndc")
+        return out_o, out_d
+
     def sample_along_rays(self, *args, **kwargs):
         raise NotImplementedError()
 
