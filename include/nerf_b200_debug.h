@@ -39,6 +39,10 @@ int nerf_debug_set_wgrad_profile(unsigned long long* buf_dev);
  * what the kernel would run at if a producer kept that operand in L2.  0 switches a wrap off. */
 int nerf_debug_set_wgrad_wrap(int64_t wrap_g, int64_t wrap_x);
 
+/* tuning aid: replaces the relative per-tile costs of the 11 wgrad work units (fc_in, fc_1..4, fc_5 position columns, fc_5 h4
+ * columns, fc_6, fc_7, fc_8, fc_9) that the static (unit, tile) partition balances by; NULL restores the built-in table. */
+int nerf_debug_set_wgrad_costs(const int* costs, int n);
+
 /* self test + rate probe of the CTA-pair MMA (tcgen05 cta_group::2, M = 256): a (256 x k), b (n x k) bf16 bits, d (256 x n)
  * fp32, all row-major; bit 0 of ts puts the A operand in tensor memory.  `pairs` clusters of two CTAs all compute the same
  * product; with iters > 0 each leader then times iters x (k/16) MMAs into cycles_dev[pair].  With bit 1 of ts (n <= 128,

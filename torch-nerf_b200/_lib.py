@@ -80,6 +80,7 @@ _DEBUG_PROTOTYPES = {
     "nerf_debug_set_profile_buffer": (c_int, [_P, c_int]),
     "nerf_debug_set_wgrad_profile": (c_int, [_P]),
     "nerf_debug_set_wgrad_wrap": (c_int, [c_int64, c_int64]),
+    "nerf_debug_set_wgrad_costs": (c_int, [POINTER(c_int), c_int]),
 }
 # ... and the building-block self tests / micro-benchmarks of libnerf_b200_selftest.so (tests/ and tools/ only)
 _SELFTEST_PROTOTYPES = {

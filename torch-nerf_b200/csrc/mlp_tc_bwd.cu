@@ -780,6 +780,7 @@ __global__ void zero_grads_kernel(ParamPtrs g) {
 
 static unsigned long long* g_wgrad_prof = nullptr;
 static int64_t g_wgrad_wrap_g = 0, g_wgrad_wrap_x = 0;
+static int g_wgrad_cost_override[kNumWUnits] = {};  // > 0: replaces the unit's cost (tuning aid, nerf_debug_set_wgrad_costs)
 
 // Per-device one-time setup (shared-memory opt-in of the kernels, the wgrad unit table in constant memory).  A process
 // that drives several GPUs must do this on each of them, hence the per-device flags.
@@ -794,6 +795,8 @@ static int bwd_device_setup() {
   NERF_CUDA(cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
   WUnit table[kNumWUnits];
   build_wunits(table);
+  for (int u = 0; u < kNumWUnits; ++u)
+    if (g_wgrad_cost_override[u] > 0) table[u].cost = g_wgrad_cost_override[u];
   NERF_CUDA(cudaMemcpyToSymbol(c_wunits, table, sizeof(table)));
   if (dev >= 0 && dev < kMaxDevices) g_bwd_ready[dev] = true;
   return NERF_OK;
@@ -849,6 +852,12 @@ using namespace nerf;
 
 extern "C" int nerf_debug_set_wgrad_profile(unsigned long long* buf_dev) {
   g_wgrad_prof = buf_dev;
+  return NERF_OK;
+}
+
+extern "C" int nerf_debug_set_wgrad_costs(const int* costs, int n) {
+  for (int u = 0; u < kNumWUnits; ++u) g_wgrad_cost_override[u] = (costs != nullptr && u < n) ? costs[u] : 0;
+  for (int d = 0; d < kMaxDevices; ++d) g_bwd_ready[d] = false;  // re-upload the unit table on the next launch
   return NERF_OK;
 }
 
