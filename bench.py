@@ -800,6 +800,11 @@ def run_b200(args):
                 dropin = dropin_block(tn, dev, n_rays, eng_render)
             except Exception as err:
                 dropin = {"unavailable": f"{type(err).__name__}: {err}"[:300]}
+        if isinstance(ref_gpu, dict) and isinstance(dropin, dict) and "c1_render_100x100_ms" in ref_gpu:
+            if "c1_render_100x100_engine_bf16_ms" in dropin:  # config C1 (100x100 frame): reference on torch-CUDA / this path
+                ref_gpu["speedup_c1_render_100x100"] = ref_gpu["c1_render_100x100_ms"] / dropin["c1_render_100x100_engine_bf16_ms"]
+            if "train_bf16" in dropin:  # and the drop-in API alone (classes swapped, reference's own loop otherwise)
+                ref_gpu["speedup_train_dropin_api"] = ref_gpu["train"]["ms_per_step"] / dropin["train_bf16"]["ms_per_step"]
         step_flop = n_rays * (SC + SC + SF) * FLOP_TRAIN_PER_EVAL
         # the whole step against both roofs: its tensor work against the sustained bf16 peak, and the HBM bytes its three
         # tensor-core kernel families move (ncu dram bytes of the fine pass's launches, recorded in profiles/traffic.json,
