@@ -56,6 +56,41 @@ def _cuda_device(device=None) -> torch.device:
     return dev
 
 
+class _PinnedStager:
+    """Host -> device copies of small index tensors without the stream synchronisation a pageable `tensor.to(device)`
+    implies (the reference keeps pixel indices on the host, volume_renderer.py:118-142; a synchronising copy at the start
+    of every pass stalls the launch queue).  A ring of pinned buffers, each guarded by the event of its last copy."""
+
+    def __init__(self, slots: int = 4):
+        self._slots = [None] * slots
+        self._next = 0
+
+    def to_device(self, t: torch.Tensor, dev: torch.device, dtype: torch.dtype) -> torch.Tensor:
+        if t.is_cuda:
+            return t.to(device=dev, dtype=dtype).contiguous()
+        src = t.detach().to(dtype).contiguous()
+        i = self._next
+        self._next = (i + 1) % len(self._slots)
+        slot = self._slots[i]
+        if slot is None or slot[0].numel() < src.numel() or slot[0].dtype != dtype:
+            buf = torch.empty((max(src.numel(), 1),), dtype=dtype, pin_memory=True)
+            slot = [buf, None]
+            self._slots[i] = slot
+        elif slot[1] is not None:
+            slot[1].synchronize()  # the copy that last used this buffer (several passes ago) has finished
+        view = slot[0][: src.numel()].view(src.shape)
+        view.copy_(src)
+        with torch.cuda.device(dev):
+            out = view.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        slot[1] = ev
+        return out
+
+
+_stager = _PinnedStager()
+
+
 def _f32_cuda(t: torch.Tensor, dev: torch.device) -> torch.Tensor:
     return t.detach().to(device=dev, dtype=torch.float32).contiguous()
 
@@ -77,7 +112,7 @@ class RaySamplerBase:
         """sampler_base.py:134-197.  pixel_coords (N,2) integer screen coordinates (CPU or CUDA)."""
         lib = _lib.load()
         dev = _cuda_device(pixel_coords.device if pixel_coords.is_cuda else None)
-        coords = pixel_coords.to(device=dev, dtype=torch.int64).contiguous()
+        coords = _stager.to_device(pixel_coords, dev, torch.int64)
         n = coords.shape[0]
         cam = pack_camera(camera, project_to_ndc)
         ray_o = torch.empty((n, 3), device=dev, dtype=torch.float32)
@@ -96,7 +131,7 @@ class RaySamplerBase:
         lib = _lib.load()
         dev = _cuda_device(device)
         if pixel_indices is not None:
-            pix = pixel_indices.to(device=dev, dtype=torch.int64).contiguous()
+            pix = _stager.to_device(pixel_indices, dev, torch.int64)
             n = pix.shape[0]
         else:
             pix, n = None, int(count)
