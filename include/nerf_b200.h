@@ -165,7 +165,7 @@ int nerf_mse_loss(const float* rgb_dev, const float* target_dev, int64_t n, floa
  *                  a multiple of 4, 16-byte aligned;  flag_ptrs[r] : rank r's pad of 2*world 32-bit flag words, zeroed once
  *   seq          : 1, 2, 3, ... identical on all ranks, incremented every call;  counter_dev : one zeroed local word
  * param_dev == NULL: exchange only (the buffers end up holding the sum, no update) -- used by the N-rank parity check.
- * Every rank of the group must make the call; a peer that never arrives traps the kernel after ~4 s instead of hanging. */
+ * Every rank of the group must make the call; a peer that never arrives traps the kernel after ~70 s instead of hanging. */
 int nerf_dp_exchange_adam(float* const* grad_ptrs, uint32_t* const* flag_ptrs, int rank, int world, float* param_dev,
                           float* exp_avg_dev, float* exp_avg_sq_dev, int64_t n, double lr, double beta1, double beta2,
                           double eps, int64_t step, double grad_scale, uint32_t seq, uint32_t* counter_dev,

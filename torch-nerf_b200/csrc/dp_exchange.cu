@@ -53,12 +53,12 @@ __device__ __forceinline__ void st_cg4(float* p, const float4& v) {
   asm volatile("st.global.cg.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// waits until flag word `p` has reached `seq` (flags only grow); ~4 s bound, then trap: a peer that never arrives must
-// not hang the GPU
+// waits until flag word `p` has reached `seq` (flags only grow); bounded (~70 s at 1.9 GHz: ranks of a real training job
+// can be seconds apart, e.g. one of them loading data), then trap: a peer that never arrives must not hang the GPU
 __device__ __forceinline__ void wait_flag(const uint32_t* p, uint32_t seq) {
   const long long t0 = clock64();
   while ((int32_t)(ld_acquire_sys(p) - seq) < 0) {
-    if (clock64() - t0 > (8ll << 30)) {
+    if (clock64() - t0 > (1ll << 37)) {
       printf("nerf_b200: data-parallel exchange timed out waiting for a peer (block %d, flag %p, want %u)\n", blockIdx.x,
              (const void*)p, seq);
       __trap();
