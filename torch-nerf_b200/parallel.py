@@ -122,8 +122,12 @@ class PeerExchange:
             raise RuntimeError("PeerExchange supports up to 16 ranks of one NVLink domain")
         self.numel = int(numel)
         padded = (self.numel + 3) // 4 * 4
-        try:  # older torch releases want the group registered first; newer ones deprecate the call
-            symm.enable_symm_mem_for_group(group.group_name)
+        try:  # older torch releases want the group registered first; newer ones deprecate the call (FutureWarning)
+            import warnings
+
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                symm.enable_symm_mem_for_group(group.group_name)
         except Exception:
             pass
         with torch.cuda.device(device):
